@@ -1,0 +1,329 @@
+"""
+CPU oracle for the radar_grid gridding hot path  —  TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+A NumPy/SciPy restatement of the reference algorithm (jgmarti84/radar-processor, ``src/radar_grid``),
+written so that it performs the *same floating-point operations in the same order and dtypes* as the
+reference does under NumPy >= 2 (NEP 50 promotion), and therefore reproduces its outputs bit for bit.
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl reference`` legs
+may import this module; the product package (``radar_grid_b200``) never does.
+
+Parity status: PINNED.  ``tests/golden/make_golden.py`` imports the real reference from
+``/root/reference`` in the build container, runs it on the seeded synthetic volumes, and commits its
+outputs under ``tests/golden/``; ``tests/test_oracle_golden.py`` checks every function below against
+those vectors bit-exactly, and ``tests/test_oracle_known_answers.py`` replays the reference's own
+known-answer unit tests (tests/test_radar_grid_{interpolate,products,filters}.py) against it.
+
+Each function cites the reference lines it follows (paths relative to /root/reference).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+from scipy.spatial import cKDTree
+
+EARTH_RADIUS = 6371000.0
+KE_DEFAULT = 4.0 / 3.0
+
+
+# --------------------------------------------------------------------------------------------------
+# a2 / a3  neighbour table          reference: src/radar_grid/compute.py:18-103 and :106-284
+# --------------------------------------------------------------------------------------------------
+
+def _weights(weighting: str, d2: np.ndarray, r2) -> np.ndarray:
+    """compute.py:82-87 — float64 arithmetic, one cast to float32 at the end."""
+    if weighting == "barnes2":
+        return (np.exp(-d2 / (r2 / 4)) + 1e-5).astype("float32")
+    if weighting == "cressman":
+        return ((r2 - d2) / (r2 + d2)).astype("float32")
+    return np.ones(d2.shape[0], dtype="float32")
+
+
+def grid_axes(grid_shape, grid_limits):
+    """compute.py:184-186 — float32 linspace, both end points included."""
+    nz, ny, nx = grid_shape
+    z = np.linspace(grid_limits[0][0], grid_limits[0][1], nz, dtype="float32")
+    y = np.linspace(grid_limits[1][0], grid_limits[1][1], ny, dtype="float32")
+    x = np.linspace(grid_limits[2][0], grid_limits[2][1], nx, dtype="float32")
+    return z, y, x
+
+
+def build_geometry(gate_x, gate_y, gate_z, grid_shape, grid_limits, radar_altitude=0.0,
+                   min_radius=250.0, beam_factor=0.01746, weighting="barnes2", toa=17000.0,
+                   z_range=None, kd_order=True):
+    """
+    Neighbour table as (indptr int64, gate_indices int32, weights float32).
+
+    Follows compute.py:182-193 (relative gate height, float32 axes, float64 voxel coordinates, TOA mask)
+    and compute.py:38-91 per level: KD-tree over the TOA-valid gates as candidate generator (:38-39,:60),
+    exact float64 test ``(dx*dx + dy*dy) + dz*dz < r*r`` (:69-74), weights (:82-87).
+    With ``kd_order=True`` each row keeps the KD-tree traversal order the reference stores; otherwise
+    rows are sorted by gate index (the canonical form used for set comparison).
+    ``z_range=(z0, z1)`` restricts the table to a z-slab (rows of levels z0..z1-1), which is how the
+    reference itself decomposes the work (compute.py:203-207).
+    """
+    if weighting not in ("barnes2", "cressman", "nearest"):
+        raise ValueError(f"Unknown weighting function: {weighting}")
+    nz, ny, nx = grid_shape
+    gate_x = np.asarray(gate_x)
+    gate_y = np.asarray(gate_y)
+    gate_z_rel = np.asarray(gate_z) - radar_altitude                      # :182 (stays float32)
+    z_ax, y_ax, x_ax = grid_axes(grid_shape, grid_limits)
+    yy, xx = np.meshgrid(y_ax, x_ax, indexing="ij")
+    vy = yy.ravel().astype("float64")                                     # :189-190
+    vx = xx.ravel().astype("float64")
+    valid = gate_z_rel <= toa                                             # :193
+    valid_ids = np.where(valid)[0]
+    gxv, gyv, gzv = gate_x[valid], gate_y[valid], gate_z_rel[valid]
+    tree = cKDTree(np.column_stack([gxv, gyv, gzv]).astype("float64"))   # :38-39
+
+    z0, z1 = (0, nz) if z_range is None else z_range
+    indptr = [0]
+    idx_chunks, w_chunks = [], []
+    for iz in range(z0, z1):
+        gz = z_ax[iz]                                                     # float32 scalar
+        vz = np.full(ny * nx, gz, dtype="float64")                        # :43
+        roi = np.maximum(min_radius, np.sqrt(vx ** 2 + vy ** 2 + vz ** 2) * beam_factor)   # :46-47
+        pts = np.column_stack([vx, vy, vz])
+        cand_lists = tree.query_ball_point(pts, roi, return_sorted=False)  # :60, traversal order
+        for i in range(ny * nx):
+            cand = cand_lists[i]
+            if not cand:
+                indptr.append(indptr[-1])
+                continue
+            loc = np.array(cand, dtype="int32")
+            r = roi[i]
+            r2 = r * r
+            dx = gxv[loc] - vx[i]                                         # float32 - float64 -> float64
+            dy = gyv[loc] - vy[i]
+            dz = gzv[loc] - vz[i]
+            d2 = dx * dx + dy * dy + dz * dz                              # :72
+            keep = d2 < r2                                                # :74 strict
+            if not np.any(keep):
+                indptr.append(indptr[-1])
+                continue
+            ids = valid_ids[loc][keep].astype("int32")
+            w = _weights(weighting, d2[keep], r2)
+            if not kd_order:
+                order = np.argsort(ids, kind="stable")
+                ids, w = ids[order], w[order]
+            idx_chunks.append(ids)
+            w_chunks.append(w)
+            indptr.append(indptr[-1] + ids.shape[0])
+    gate_indices = np.concatenate(idx_chunks) if idx_chunks else np.zeros(0, "int32")
+    weights = np.concatenate(w_chunks) if w_chunks else np.zeros(0, "float32")
+    return np.asarray(indptr, dtype="int64"), gate_indices.astype("int32"), weights.astype("float32")
+
+
+def neighbours_bruteforce(gate_x, gate_y, gate_z, voxel_xyz, radar_altitude=0.0, min_radius=250.0,
+                          beam_factor=0.01746, weighting="barnes2", toa=17000.0):
+    """
+    Exact neighbour set of ONE voxel by testing every gate — no spatial index, so it is independent of
+    the KD-tree candidate generator (used to spot-check full-size configs on sampled voxels).
+    ``voxel_xyz`` are the float32 axis values (widened to float64 exactly as compute.py:43,189-190 do).
+    Returns (sorted gate ids int32, weights float32 in that order).
+    """
+    vx, vy, vz = (np.float64(np.float32(c)) for c in voxel_xyz)
+    gz_rel = np.asarray(gate_z) - radar_altitude
+    valid_ids = np.where(gz_rel <= toa)[0]
+    r = np.maximum(min_radius, np.sqrt(vx ** 2 + vy ** 2 + vz ** 2) * beam_factor)
+    r2 = r * r
+    dx = np.asarray(gate_x)[valid_ids] - vx
+    dy = np.asarray(gate_y)[valid_ids] - vy
+    dz = gz_rel[valid_ids] - vz
+    d2 = dx * dx + dy * dy + dz * dz
+    keep = d2 < r2
+    return valid_ids[keep].astype("int32"), _weights(weighting, d2[keep], r2)
+
+
+def canonical_rows(indptr, gate_indices, weights):
+    """Sort every CSR row by gate id (stable) so that two tables can be compared as sets."""
+    indptr = np.asarray(indptr, dtype=np.int64)
+    n_rows = indptr.shape[0] - 1
+    row_of = np.repeat(np.arange(n_rows, dtype=np.int64), np.diff(indptr))
+    order = np.lexsort((gate_indices, row_of))
+    return gate_indices[order], weights[order]
+
+
+# --------------------------------------------------------------------------------------------------
+# a4 / a5  CSR gather-weighted mean      reference: src/radar_grid/interpolate.py:15-104, 107-142
+# --------------------------------------------------------------------------------------------------
+
+def apply_geometry(indptr, gate_indices, weights, grid_shape, field_data, extra_masks=(), fill_value=np.nan):
+    """
+    interpolate.py:59-104.  ``field_data`` is a (masked) array of length n_gates, ``extra_masks`` the
+    ``gate_excluded`` arrays of any GateFilters (OR-ed into the field mask, :60-61).
+    Masked gates contribute weight 0 and value 0 (:78-79); products are float32 (:82); segment sums use
+    ``np.add.reduceat`` over the non-empty rows (:85-93), i.e. ``v[0] + pairwise_sum(v[1:])`` per row;
+    a voxel is ``fill_value`` when it has no gates or its effective weight sum is not > 0 (:99-102).
+    """
+    n_grid = int(np.prod(grid_shape))
+    mask = np.ma.getmask(field_data)
+    for m in extra_masks:
+        mask = mask | m
+    data = np.ma.getdata(field_data)
+    vals = data[gate_indices]
+    msk = mask[gate_indices]
+    safe_v = np.where(msk, 0.0, vals)
+    eff_w = np.where(msk, 0.0, weights)
+    wv = eff_w * safe_v
+    seg_len = np.diff(indptr)
+    rows = np.where(seg_len > 0)[0]
+    starts = np.asarray(indptr)[:-1][seg_len > 0]
+    out = np.full(n_grid, fill_value, dtype="float32")
+    if starts.shape[0]:
+        s_wv = np.add.reduceat(wv, starts)
+        s_w = np.add.reduceat(eff_w, starts)
+        ok = s_w > 0
+        out[rows[ok]] = s_wv[ok] / s_w[ok]
+    return out.reshape(grid_shape)
+
+
+# --------------------------------------------------------------------------------------------------
+# a6  gate filters                        reference: src/radar_grid/filters.py:91-237
+# --------------------------------------------------------------------------------------------------
+
+def filter_values(field_2d) -> np.ndarray:
+    """filters.py:91-102 — raw float32 values, NaN/Inf left in place (so they compare False)."""
+    return np.ma.getdata(np.ma.masked_invalid(field_2d)).ravel().astype("float32")
+
+
+def exclude_below(field_2d, thr):
+    return filter_values(field_2d) < thr          # filters.py:133-134
+
+
+def exclude_above(field_2d, thr):
+    return filter_values(field_2d) > thr          # filters.py:156-157
+
+
+def exclude_outside(field_2d, lo, hi):
+    v = filter_values(field_2d)                   # filters.py:208-209
+    return (v < lo) | (v > hi)
+
+
+# --------------------------------------------------------------------------------------------------
+# a7  column reductions                   reference: src/radar_grid/products.py:420-580
+# --------------------------------------------------------------------------------------------------
+
+def _z_slice(grid, z_min_idx, z_max_idx, z_min_alt, z_max_alt, grid_limits):
+    nz = grid.shape[0]
+    if z_min_alt is not None or z_max_alt is not None:
+        if grid_limits is None:
+            raise ValueError("geometry is required when using altitude-based limits")
+        zc = np.linspace(grid_limits[0][0], grid_limits[0][1], nz)       # float64, :469
+        if z_min_alt is not None:
+            z_min_idx = np.searchsorted(zc, z_min_alt)
+        if z_max_alt is not None:
+            z_max_idx = np.searchsorted(zc, z_max_alt, side="right") - 1
+    z_min_idx = 0 if z_min_idx is None else z_min_idx
+    z_max_idx = nz - 1 if z_max_idx is None else z_max_idx
+    return max(0, z_min_idx), min(nz - 1, z_max_idx)
+
+
+def column_reduce(kind, grid, z_min_idx=None, z_max_idx=None, z_min_alt=None, z_max_alt=None, grid_limits=None):
+    """products.py:462-490 (max), :509-535 (min), :554-580 (mean): nan-ignoring reductions over z."""
+    lo, hi = _z_slice(grid, z_min_idx, z_max_idx, z_min_alt, z_max_alt, grid_limits)
+    sl = grid[lo:hi + 1]
+    with np.errstate(all="ignore"):
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)
+            return {"max": np.nanmax, "min": np.nanmin, "mean": np.nanmean}[kind](sl, axis=0)
+
+
+# --------------------------------------------------------------------------------------------------
+# a8  CAPPI                               reference: src/radar_grid/products.py:317-415
+# --------------------------------------------------------------------------------------------------
+
+def cappi(grid, grid_shape, grid_limits, altitude, interpolation="linear"):
+    nz, ny, nx = grid_shape
+    z_min, z_max = grid_limits[0]
+    zc = np.linspace(z_min, z_max, nz, dtype="float32")                  # :367
+    if altitude < z_min or altitude > z_max:                              # :370-372
+        return np.full((ny, nx), np.nan, dtype="float32")
+    if interpolation == "nearest":
+        return grid[np.argmin(np.abs(zc - altitude))]                     # :377-378
+    if interpolation != "linear":
+        raise ValueError(f"Unknown interpolation method: {interpolation}")
+    hit = np.isclose(zc, altitude, rtol=1e-6)                             # :382-386
+    if np.any(hit):
+        return grid[np.where(hit)[0][0]]
+    z_step = (z_max - z_min) / (nz - 1) if nz > 1 else 1.0
+    z_frac = (altitude - z_min) / z_step
+    lo = int(np.floor(z_frac))
+    hi = lo + 1
+    if lo < 0:
+        return grid[0]
+    if hi >= nz:
+        return grid[nz - 1]
+    w_hi = z_frac - lo
+    w_lo = 1.0 - w_hi
+    return (w_lo * grid[lo] + w_hi * grid[hi]).astype("float32")          # :411-412
+
+
+# --------------------------------------------------------------------------------------------------
+# a9  constant-elevation PPI              reference: src/radar_grid/products.py:23-89, 139-165, 168-314
+# --------------------------------------------------------------------------------------------------
+
+def beam_height(horizontal_distance, elevation_angle, radar_altitude=0.0, ke=KE_DEFAULT, re=EARTH_RADIUS):
+    """products.py:70-89."""
+    e = np.radians(elevation_angle)
+    ke_re = ke * re
+    sr = horizontal_distance / np.maximum(np.cos(e), 0.01)
+    return np.sqrt(sr ** 2 + ke_re ** 2 + 2 * sr * ke_re * np.sin(e)) - ke_re + radar_altitude
+
+
+def beam_height_flat(horizontal_distance, elevation_angle, radar_altitude=0.0):
+    """products.py:164-165."""
+    return horizontal_distance * np.tan(np.radians(elevation_angle)) + radar_altitude
+
+
+def ppi(grid, grid_shape, grid_limits, elevation_angle, interpolation="linear", earth_curvature=True,
+        ke=KE_DEFAULT):
+    nz, ny, nx = grid_shape
+    z_min, z_max = grid_limits[0]
+    yc = np.linspace(grid_limits[1][0], grid_limits[1][1], ny, dtype="float32")   # :227-228
+    xc = np.linspace(grid_limits[2][0], grid_limits[2][1], nx, dtype="float32")
+    yy, xx = np.meshgrid(yc, xc, indexing="ij")
+    hdist = np.sqrt(xx ** 2 + yy ** 2)                                    # float32, :235
+    tz = (beam_height(hdist, elevation_angle, 0.0, ke) if earth_curvature
+          else beam_height_flat(hdist, elevation_angle, 0.0))             # :238-251
+    z_step = (z_max - z_min) / (nz - 1) if nz > 1 else 1.0
+    yi, xi = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
+    if interpolation == "nearest":                                        # :256-272
+        zi = np.round((tz - z_min) / z_step).astype(int)
+        ok = (zi >= 0) & (zi < nz)
+        out = grid[np.clip(zi, 0, nz - 1), yi, xi]
+        out[~ok] = np.nan
+        return out
+    if interpolation != "linear":
+        raise ValueError(f"Unknown interpolation method: {interpolation}")
+    z_frac = (tz - z_min) / z_step                                        # :279-309
+    lo = np.floor(z_frac).astype(int)
+    hi = lo + 1
+    w_hi = z_frac - lo
+    w_lo = 1.0 - w_hi
+    v_lo = grid[np.clip(lo, 0, nz - 1), yi, xi]
+    v_hi = grid[np.clip(hi, 0, nz - 1), yi, xi]
+    out = w_lo * v_lo + w_hi * v_hi
+    out[tz < z_min] = np.nan
+    out[tz > z_max] = np.nan
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# a10  GridFilter                         reference: src/radar_grid/filters.py:631-780
+# --------------------------------------------------------------------------------------------------
+
+def grid_filter(kind, plane, a=None, b=None, fill_value=np.nan):
+    out = plane.copy()
+    if kind == "below":
+        out[out < a] = fill_value
+    elif kind == "above":
+        out[out > a] = fill_value
+    elif kind == "outside":
+        out[(out < a) | (out > b)] = fill_value
+    elif kind == "invalid":
+        out[np.isnan(out) | np.isinf(out)] = fill_value
+    else:
+        raise ValueError(kind)
+    return out

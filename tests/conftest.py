@@ -1,0 +1,50 @@
+"""pytest configuration: marker registration, import paths, shared fixtures."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG_ROOT = os.path.join(ROOT, "radar-processor_b200")
+for p in (ROOT, PKG_ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def load_golden(name):
+    with np.load(os.path.join(GOLDEN, name)) as z:
+        return {k: z[k] for k in z.files}
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return load_golden
+
+
+def golden_case(spec_name, weighting="barnes2", alt=0):
+    """(spec, radar, gates, fields, golden dict) for one committed reference fixture."""
+    from radar_grid_b200 import synthetic as S
+    spec = S.SPECS[spec_name]
+    radar = S.SyntheticRadar(spec, seed=7, radar_altitude=float(alt))
+    gx = radar.gate_x["data"].ravel().astype("float32")
+    gy = radar.gate_y["data"].ravel().astype("float32")
+    gz = radar.gate_z["data"].ravel().astype("float32")
+    fields = {k: np.ma.masked_invalid(v["data"]).ravel().astype("float32") for k, v in radar.fields.items()}
+    g = load_golden(f"ref_{spec_name}_{weighting}_alt{int(alt)}.npz")
+    return spec, radar, (gx, gy, gz), fields, g
+
+
+def assert_same(a, b, what=""):
+    """Bit-level equality including NaN positions (NaN payloads are not compared)."""
+    a = np.asarray(a)
+    b = np.asarray(b)
+    assert a.shape == b.shape, f"{what}: shape {a.shape} != {b.shape}"
+    assert a.dtype == b.dtype, f"{what}: dtype {a.dtype} != {b.dtype}"
+    np.testing.assert_array_equal(a, b, err_msg=what)
