@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""
+bench.py — headline benchmark of the gridding hot path (BASELINE.json metric: voxels/s for interpolation +
+COLMAX(+CAPPI), fraction of the HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg3|cfg1|small]
+
+Workload (N=1): BASELINE.json configs[2] — the configuration the north-star target is quoted on: a 15-sweep x
+360 x 1000-gate volume with five fields (DBZH, ZDR, RHOHV, KDP, VRAD) gridded onto 40x481x481 at 0.5 km through
+ONE shared neighbour table; a step = one volume: gate-mask fusion + record packing (K4), fused 5-field CSR
+interpolation writing the five 3-D grids, with COLMAX and CAPPI(4000 m) in the epilogue (K5+K6).
+The neighbour table is built once on the GPU before the timed region (it is amortised over every volume of a
+scan strategy; its build time is reported in `config`).  Data are synthetic, seeded.
+
+N>1: weak scaling, no data-path collective — every rank holds a replica of the table and grids its own
+volumes (the reference's time-series batch shard, BASELINE.json configs[3]); value = all ranks' voxels /
+max-over-ranks device time.
+
+--impl reference times the CPU path (the NumPy oracle port of the pure-Python reference, see oracle/) on a
+bounded sample of the same workload on the box's host cores.
+"""
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "radar-processor_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "voxels/sec (interp+COLMAX+CAPPI, voxel-fields gridded per second)"
+UNIT = "voxels/s"
+CAPPI_ALT = 4000.0
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def algorithmic_bytes(P, V, G, F, ncol, grids=True, n_planes=2):
+    """8P + 4(V+1) + 5FG + B_out, B_out = 4FV for the 3-D grids + 4F*ny*nx per 2-D product."""
+    return 8 * P + 4 * (V + 1) + 5 * F * G + (4 * F * V if grids else 0) + n_planes * 4 * F * ncol
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks: sampled DURING the timed region
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, device_index):
+        self.idx = device_index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._th = None
+        self._nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nv = None
+
+    def _loop(self):
+        nv = self._nv
+        names = {}
+        for n in dir(nv):
+            if n.startswith("nvmlClocksEventReason") or n.startswith("nvmlClocksThrottleReason"):
+                try:
+                    names[int(getattr(nv, n))] = n.replace("nvmlClocksEventReason", "").replace("nvmlClocksThrottleReason", "")
+                except Exception:
+                    pass
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                try:
+                    bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+                except Exception:
+                    bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                for b, n in names.items():
+                    if b and bits & b and n not in ("None", "GpuIdle", "All"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.01)
+
+    def start(self):
+        if self._nv is not None:
+            self._th = threading.Thread(target=self._loop, daemon=True)
+            self._th.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._th is not None:
+            self._th.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unsampled"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------
+def raw_fields(spec, seed, gates):
+    from radar_grid_b200 import synthetic as S
+    fields = S.make_fields(spec, seed=seed, gates=gates)
+    out = []
+    for name in spec.fields:
+        v = np.ma.getdata(fields[name]).astype(np.float32).copy()
+        v[np.ma.getmaskarray(fields[name])] = np.nan       # the device re-derives the masks (masked_invalid)
+        out.append(v)
+    return fields, out
+
+
+def run_b200(args):
+    import torch
+    import radar_grid_b200 as rg
+    from radar_grid_b200 import _native as N, synthetic as S
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if N.device_count() < 1 or not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: radar_grid_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    spec = S.SPECS[args.workload]
+    F = len(spec.fields)
+    nz, ny, nx = spec.grid_shape
+    V, ncol, G = nz * ny * nx, ny * nx, spec.n_gates
+
+    stream = torch.cuda.Stream()
+    ctx = N.Context(local_rank, stream.cuda_stream)
+    gates = S.gate_coordinates(spec)
+    t0 = time.perf_counter()
+    dev = rg.DeviceGeometry.build(*gates, spec.grid_shape, spec.grid_limits, min_radius=spec.min_radius,
+                                  beam_factor=spec.beam_factor, weighting=spec.weighting, toa=spec.toa, ctx=ctx)
+    build_wall = time.perf_counter() - t0
+    info = dev.info
+    P = dev.n_pairs
+
+    fields_ma, raw = raw_fields(spec, seed=rank, gates=gates)
+    products = [rg.ColumnMax(), rg.CAPPI(CAPPI_ALT)]
+
+    with torch.cuda.stream(stream):
+        dfields = [torch.from_numpy(r).cuda(non_blocking=False) for r in raw]
+        out_grids = [torch.empty((nz, ny, nx), dtype=torch.float32, device="cuda") for _ in range(F)]
+        out_prods = [torch.empty((F, ny, nx), dtype=torch.float32, device="cuda") for _ in products]
+
+        def step():
+            rg.grid_fields(dev, dfields, mask_invalid=True, products=products, want_grid=True, ctx=ctx,
+                           out_grids=out_grids, out_products=out_prods)
+
+        for _ in range(args.warmup):
+            step()
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        launches0 = ctx.kernel_launches()
+        ctx.set_option("timing", 1)
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step()
+        ev1.record(stream)
+        stream.synchronize()
+        torch.cuda.synchronize()
+        clocks = sampler.stop()
+        elapsed_ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            dist.barrier()
+        ctx.set_option("timing", 0)
+        launches = ctx.kernel_launches() - launches0
+        apply_ms, n_apply = ctx.kernel_time(1)
+        pack_ms, n_pack = ctx.kernel_time(0)
+        if world > 1:
+            t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            elapsed_ms = float(t.item())
+
+        # ---- end-to-end: host buffers in, host buffers out, through the public API (copies inside the call)
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        pin_in = []
+        for r in raw:
+            a = rg.pinned_empty(r.shape, np.float32)
+            a[:] = r
+            pin_in.append(a)
+        pin_grids = [rg.pinned_empty((nz, ny, nx), np.float32) for _ in range(F)]
+        pin_prods = [rg.pinned_empty((F, ny, nx), np.float32) for _ in products]
+
+        def e2e_step():
+            rg.grid_fields(dev, pin_in, mask_invalid=True, products=products, want_grid=True, ctx=ctx,
+                           out_grids=pin_grids, out_products=pin_prods)
+
+        for _ in range(2):
+            e2e_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()                      # synchronous: returns when the results are in host memory
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        h2d = F * G * 4
+        d2h = F * V * 4 + len(products) * F * ncol * 4
+        # parity spot check of what the timed path produced (device outputs vs host-path outputs)
+        same = all(torch.equal(out_grids[f].cpu().nan_to_num(-1e30), torch.from_numpy(pin_grids[f]).nan_to_num(-1e30))
+                   for f in range(F))
+
+    ms_per_step = elapsed_ms / args.steps
+    value = world * F * V / (ms_per_step * 1e-3)
+    peak, peak_src = load_peaks()
+    b_alg = algorithmic_bytes(P, V, G, F, ncol)
+    apply_avg_ms = apply_ms / max(n_apply, 1)
+    achieved = b_alg / (apply_avg_ms * 1e-3) / 1e9 if apply_avg_ms > 0 else None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic (seeded storm-cell volume, SURVEY.md 8d)",
+        "config": {
+            "workload": f"{spec.name}: {len(spec.elevations)} sweeps x {spec.nrays} x {spec.ngates} gates, fields "
+                        f"{'+'.join(spec.fields)} -> {nz}x{ny}x{nx} grid, one shared neighbour table ({spec.weighting}); "
+                        f"per step: mask+pack, {F}-field 3-D grids + COLMAX + CAPPI {CAPPI_ALT:.0f} m",
+            "volumes_per_s": world / (ms_per_step * 1e-3),
+            "pairs": P, "voxels": V, "gates": G, "fields": F,
+            "l2_policy": "inputs larger than L2 (8P-byte pair stream = %.2f GB per step)" % (8 * P / 1e9),
+            "parallelism": f"volume-batch shard x{world}, table replicated, no data-path collective",
+            "geometry_build_ms_device": info["build_ms"], "geometry_build_s_wall": build_wall,
+            "geometry_candidates_per_pair": info["n_candidates"] / max(P, 1),
+            "pack_ms_per_step": pack_ms / max(n_pack, 1), "apply_ms_per_step": apply_avg_ms,
+            "device_vs_host_path_identical": bool(same),
+        },
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": None,
+                     "kernel": "apply_columns_kernel", "algorithmic_bytes": b_alg, "peak_source": peak_src,
+                     "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None},
+        "clocks": clocks,
+        "e2e": {"value": world * F * V * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
+                "note": "pinned host fields in, 3-D grids + COLMAX + CAPPI planes back to pinned host memory, "
+                        "through grid_fields() -> rg_apply(RG_HOST)"},
+        "gpu_launches": launches,
+    }
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_from_table(dev, spec, fields_ma)
+    if world > 1:
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_from_table(dev, spec, fields_ma):
+    """The oracle port (NumPy, same arithmetic as the reference) on ONE field over the full table, 1 core."""
+    from oracle import radar_grid_oracle as O
+    indptr, idx, w = dev.export_csr()
+    nz, ny, nx = spec.grid_shape
+    name = spec.fields[0]
+    t0 = time.perf_counter()
+    grid = O.apply_geometry(indptr, idx, w, spec.grid_shape, fields_ma[name])
+    O.column_reduce("max", grid)
+    O.cappi(grid, spec.grid_shape, spec.grid_limits, CAPPI_ALT)
+    dt = time.perf_counter() - t0
+    return {"value": nz * ny * nx / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"1 of {len(spec.fields)} fields ({name}) over the full {nz}x{ny}x{nx} grid and table: apply_geometry + "
+                      f"column_max + CAPPI, single-threaded NumPy as in the reference ({dt:.2f} s)",
+            "host_cpus": os.cpu_count()}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference arm: the CPU path (oracle port of the pure-Python reference) on the host cores
+# ---------------------------------------------------------------------------------------------------------
+_REF = {}
+
+
+def _ref_build_level(iz):
+    from oracle import radar_grid_oracle as O
+    s = _REF["spec"]
+    return iz, O.build_geometry(*_REF["gates"], s.grid_shape, s.grid_limits, min_radius=s.min_radius,
+                                beam_factor=s.beam_factor, weighting=s.weighting, toa=s.toa, z_range=(iz, iz + 1))
+
+
+def _ref_apply(task):
+    from oracle import radar_grid_oracle as O
+    iz, name = task
+    s = _REF["spec"]
+    indptr, idx, w = _REF["tables"][iz]
+    return iz, name, O.apply_geometry(indptr, idx, w, (1, s.grid_shape[1], s.grid_shape[2]), _REF["fields"][name])
+
+
+def run_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import multiprocessing as mp
+    from radar_grid_b200 import synthetic as S
+    from oracle import radar_grid_oracle as O
+    spec = S.SPECS[args.workload]
+    nz, ny, nx = spec.grid_shape
+    F = len(spec.fields)
+    cores = os.cpu_count() or 1
+    # bounded sample: keep the whole --steps/--warmup run within a few minutes whatever K and W are
+    budget_s = 150.0 / max(1, args.steps + args.warmup)
+    n_levels = int(max(1, min(5, budget_s / 0.4, nz)))
+    step_z = max(1, nz // n_levels)
+    levels = list(range(0, nz, step_z))[:n_levels]
+    cappi_level = int(round((CAPPI_ALT - spec.grid_limits[0][0]) / ((spec.grid_limits[0][1] - spec.grid_limits[0][0]) / (nz - 1))))
+    if cappi_level not in levels and 0 <= cappi_level < nz:
+        levels[1 if len(levels) > 1 else 0] = cappi_level
+        levels = sorted(set(levels))
+    gates = S.gate_coordinates(spec)
+    _REF.update(spec=spec, gates=gates)
+    ctxmp = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctxmp.Pool(min(cores, len(levels))) as pool:
+        _REF["tables"] = dict(pool.map(_ref_build_level, levels))
+    build_s = time.perf_counter() - t0
+    _REF["fields"] = S.make_fields(spec, seed=0, gates=gates)
+    tasks = [(iz, name) for iz in levels for name in spec.fields]
+    workers = min(cores, len(tasks))
+    pairs = sum(int(t[0][-1]) for t in _REF["tables"].values())
+
+    def step(pool):
+        grids = {}
+        for iz, name, g in pool.map(_ref_apply, tasks):
+            grids[(iz, name)] = g[0]
+        for name in spec.fields:
+            stack = np.stack([grids[(iz, name)] for iz in levels])
+            O.column_reduce("max", stack)
+            _ = stack[levels.index(cappi_level)] if cappi_level in levels else None
+
+    with ctxmp.Pool(workers) as pool:
+        for _ in range(args.warmup):
+            step(pool)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step(pool)
+        dt = time.perf_counter() - t0
+    value = F * len(levels) * ny * nx * args.steps / dt
+    sample = (f"z-levels {levels} of {nz} (table built by the oracle in {build_s:.0f} s, untimed), all {F} fields: "
+              f"apply_geometry per (level, field) + COLMAX over the sampled levels + CAPPI level pick; "
+              f"{workers} worker processes")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded storm-cell volume, SURVEY.md 8d)",
+        "config": {"workload": f"{spec.name}: CPU path of the reference (NumPy oracle port; the reference is pure Python, "
+                               f"nothing to compile into oracle/_ref), bounded sample", "pairs_in_sample": pairs},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample,
+                         "host_cpus": cores},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg1", "cfg2", "small", "tiny"])
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.steps = 3 if args.steps is None else max(1, args.steps)
+        args.warmup = 1 if args.warmup is None else max(0, args.warmup)
+        run_reference(args)
+    else:
+        args.steps = 200 if args.steps is None else max(1, args.steps)
+        args.warmup = 10 if args.warmup is None else max(3, args.warmup)
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

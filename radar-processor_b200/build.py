@@ -1,0 +1,77 @@
+#!/usr/bin/env python
+"""
+Build libradargrid_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python radar-processor_b200/build.py [--force] [--variant NAME -DFLAG ...]
+
+The library has no torch / Python dependency: it is a plain C-ABI shared object (include/radar_grid_b200.h)
+that the Python mirror loads with ctypes.  Built files live under radar-processor_b200/lib/ (git-ignored,
+but they travel to the GPU box with the gpurun snapshot).
+"""
+import argparse
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SRC = [os.path.join(HERE, "csrc", f) for f in ("rg_api.cu", "rg_apply.cu", "rg_geometry.cu")]
+HDR = [os.path.join(HERE, "csrc", "rg_internal.cuh"), os.path.join(ROOT, "include", "radar_grid_b200.h")]
+LIBDIR = os.path.join(HERE, "lib")
+
+NVCC_FLAGS = [
+    "-O3", "-std=c++17",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo",
+    "-fmad=false",            # parity: no silent FMA contraction; the fast kernel asks for fmaf explicitly
+    "-Xcompiler", "-fPIC", "-shared",
+    "-I", os.path.join(ROOT, "include"),
+]
+
+
+def lib_path(variant=""):
+    return os.path.join(LIBDIR, f"libradargrid_b200{('_' + variant) if variant else ''}.so")
+
+
+def _digest(extra):
+    h = hashlib.sha256()
+    for f in SRC + HDR + [os.path.abspath(__file__)]:
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(extra).encode())
+    return h.hexdigest()
+
+
+def build(force=False, variant="", extra_flags=(), verbose=False):
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    os.makedirs(LIBDIR, exist_ok=True)
+    out = lib_path(variant)
+    stamp = out + ".sha256"
+    digest = _digest(list(extra_flags))
+    if not force and os.path.exists(out) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
+        return out
+    if not os.path.exists(nvcc):
+        if os.path.exists(out):
+            return out          # GPU box without the sources' toolchain: use the shipped binary
+        raise RuntimeError("nvcc not found and no prebuilt libradargrid_b200.so")
+    cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + SRC
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed")
+    if verbose:
+        sys.stderr.write(res.stderr)
+    with open(stamp, "w") as fh:
+        fh.write(digest)
+    return out
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("--variant", default="")
+    ap.add_argument("--verbose", action="store_true")
+    args, extra = ap.parse_known_args()
+    print(build(force=args.force, variant=args.variant, extra_flags=extra, verbose=args.verbose))

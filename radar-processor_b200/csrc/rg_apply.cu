@@ -1,0 +1,613 @@
+// K4 (gate-mask fusion + record packing), K5 (CSR gather-weighted mean) and K6 (COLMAX / CAPPI / PPI,
+// fused as the epilogue of K5 or run stand-alone on an existing 3-D grid).
+//
+// Reference arithmetic being replaced (paths relative to the reference repo):
+//   src/radar_grid/interpolate.py:59-104   apply_geometry
+//   src/radar_grid/filters.py:114-211      GateFilter.exclude_below / exclude_above / exclude_outside
+//   src/radar_grid/products.py:168-314     constant_elevation_ppi (+ compute_beam_height :70-89, _flat :164-165)
+//   src/radar_grid/products.py:317-415     constant_altitude_ppi
+//   src/radar_grid/products.py:420-580     column_max / column_min / column_mean
+//
+// Data layout in HBM
+//   pairs   uint2[P]      {gate id, float32 weight bits}  — one 8-byte stream, read exactly once per apply
+//   indptr  uint32[V+1]   row v = (lz*ny + iy)*nx + ix
+//   records float[G][FP]  FP = 1/2/4/8 floats per gate: the F field values of a gate side by side, so a
+//                         single 4..32-byte gather serves every field; a masked value is the bit pattern
+//                         kMaskedBits.  The record array is small (<= 32 B * G) and is re-read ~P/G times:
+//                         it is meant to live in L2 while the pair stream goes past it with evict-first
+//                         loads.
+// Mapping
+//   A CTA owns 256/W consecutive columns (flattened iy*nx + ix); a group of W lanes owns one column and
+//   walks its levels bottom-up.  For one level the CTA's rows are consecutive CSR rows, so the pair
+//   stream is read in contiguous multi-KB runs.  Because a group sees every level of its column, the
+//   column products (running max, the two levels of a CAPPI/PPI blend) are kept in registers and written
+//   once: a products-only request never writes the 3-D grid.
+
+#include <math.h>
+
+#include "rg_internal.cuh"
+
+namespace rg {
+
+// ------------------------------------------------------------------------------------------------------
+// K4  pack: gate masks (field mask | masked_invalid | fused QC range rules) + AoS records
+// ------------------------------------------------------------------------------------------------------
+template <int FP>
+__global__ void __launch_bounds__(256) pack_records_kernel(const __grid_constant__ PackParams p)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= p.n_gates) return;
+
+    // one exclusion bit per field from the fused range rules (filters.py:133-134, 156-157, 208-209)
+    uint32_t excluded = 0;
+    for (int r = 0; r < p.n_rules; ++r) {
+        const float q = __ldg(p.rule_values[r] + g);
+        const bool hit = (p.rule_use_lo[r] && q < p.rule_lo[r]) || (p.rule_use_hi[r] && q > p.rule_hi[r]);
+        if (hit) excluded |= p.rule_bits[r];
+    }
+
+    float out[FP];
+#pragma unroll
+    for (int f = 0; f < FP; ++f) {
+        uint32_t bits = kMaskedBits;
+        if (f < p.n_fields) {
+            const float v = __ldg(p.fields[f] + g);
+            bool masked = (excluded >> f) & 1u;
+            if (p.masks[f] != nullptr) masked |= __ldg(p.masks[f] + g) != 0;
+            if ((p.invalid_bits >> f) & 1u) masked |= !isfinite(v);          // np.ma.masked_invalid
+            bits = masked ? kMaskedBits : (isnan(v) ? kCanonNaN : __float_as_uint(v));
+        }
+        out[f] = __uint_as_float(bits);
+    }
+    float* dst = p.records + (size_t)g * FP;
+    if constexpr (FP == 1) {
+        dst[0] = out[0];
+    } else if constexpr (FP == 2) {
+        *reinterpret_cast<float2*>(dst) = make_float2(out[0], out[1]);
+    } else if constexpr (FP == 4) {
+        *reinterpret_cast<float4*>(dst) = make_float4(out[0], out[1], out[2], out[3]);
+    } else {
+        reinterpret_cast<float4*>(dst)[0] = make_float4(out[0], out[1], out[2], out[3]);
+        reinterpret_cast<float4*>(dst)[1] = make_float4(out[4], out[5], out[6], out[7]);
+    }
+}
+
+int records_width(int n_fields) { return n_fields <= 1 ? 1 : n_fields == 2 ? 2 : n_fields <= 4 ? 4 : 8; }
+
+int launch_pack(Context* ctx, const PackParams& p)
+{
+    if (p.n_gates == 0) return RG_OK;
+    const unsigned blocks = (unsigned)((p.n_gates + 255) / 256);
+    timer_begin(ctx, kTimerPack);
+    switch (records_width(p.n_fields)) {
+        case 1: pack_records_kernel<1><<<blocks, 256, 0, ctx->stream>>>(p); break;
+        case 2: pack_records_kernel<2><<<blocks, 256, 0, ctx->stream>>>(p); break;
+        case 4: pack_records_kernel<4><<<blocks, 256, 0, ctx->stream>>>(p); break;
+        default: pack_records_kernel<8><<<blocks, 256, 0, ctx->stream>>>(p); break;
+    }
+    timer_end(ctx, kTimerPack);
+    ctx->launches++;
+    RG_CUDA(cudaGetLastError());
+    return RG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K6  per-column product state, shared by the fused epilogue and the stand-alone kernel so that both
+//     give bit-identical planes
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double beam_target_z(const SliceParams& s, float x, float y)
+{
+    // products.py:235  horizontal_dist = sqrt(xx**2 + yy**2) in float32
+    const float h = __fsqrt_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)));
+    if (s.curvature) {
+        // products.py:80-87 in float64 (float32 array / np.float64 scalar promotes)
+        const double sr = __ddiv_rn((double)h, s.cos_c);
+        const double a = __dadd_rn(__dmul_rn(sr, sr), s.ke_re_sq);
+        const double b = __dmul_rn(__dmul_rn(__dmul_rn(2.0, sr), s.ke_re), s.sin_e);
+        return __dadd_rn(__dsub_rn(__dsqrt_rn(__dadd_rn(a, b)), s.ke_re), 0.0);
+    }
+    return __dadd_rn(__dmul_rn((double)h, s.tan_e), 0.0);   // products.py:165
+}
+
+__device__ __forceinline__ int clampi(double v, int lo, int hi)
+{
+    if (!(v >= (double)lo)) return lo;     // also catches NaN
+    if (v > (double)hi) return hi;
+    return (int)v;
+}
+
+struct ColumnState {
+    float cmax, cmin, msum;
+    int mcnt;
+    float s_lo[RG_MAX_SLICES], s_hi[RG_MAX_SLICES];
+    int zz[RG_MAX_SLICES];               // captured levels: lo | hi << 16
+
+    __device__ __forceinline__ void init(const ProductParams& pp, float x, float y)
+    {
+        cmax = cmin = __uint_as_float(kCanonNaN);
+        msum = 0.f;
+        mcnt = 0;
+#pragma unroll
+        for (int k = 0; k < RG_MAX_SLICES; ++k) {
+            s_lo[k] = s_hi[k] = __uint_as_float(kCanonNaN);
+            zz[k] = 0;
+            if (k < pp.n_slices) {
+                const SliceParams& s = pp.slices[k];
+                int lo, hi;
+                if (s.kind == RG_PROD_BEAM) {
+                    const double tz = beam_target_z(s, x, y);
+                    const double zf = __ddiv_rn(__dsub_rn(tz, pp.z_min), pp.z_step);
+                    if (s.mode == 1) {           // 'nearest'  products.py:259-264
+                        lo = hi = clampi(rint(zf), 0, pp.nz_full - 1);
+                    } else {                     // 'linear'   products.py:279-292
+                        const double fl = floor(zf);
+                        lo = clampi(fl, 0, pp.nz_full - 1);
+                        hi = clampi(fl + 1.0, 0, pp.nz_full - 1);
+                    }
+                } else {
+                    lo = s.z_lo;
+                    hi = s.z_hi;
+                }
+                zz[k] = lo | (hi << 16);
+            }
+        }
+    }
+
+    // v is the finished voxel value of GLOBAL level z; levels must arrive in ascending order
+    __device__ __forceinline__ void update(const ProductParams& pp, int z, float v)
+    {
+        const bool ok = !isnan(v);
+        if (pp.cmax_on && z >= pp.cmax_z0 && z <= pp.cmax_z1 && ok) cmax = isnan(cmax) ? v : fmaxf(cmax, v);
+        if (pp.cmin_on && z >= pp.cmin_z0 && z <= pp.cmin_z1 && ok) cmin = isnan(cmin) ? v : fminf(cmin, v);
+        if (pp.cmean_on && z >= pp.cmean_z0 && z <= pp.cmean_z1) {
+            // np.nanmean: NaN -> 0, sequential float32 adds along z, count of non-NaN
+            msum = __fadd_rn(msum, ok ? v : 0.f);
+            mcnt += ok ? 1 : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < RG_MAX_SLICES; ++k) {
+            if (k < pp.n_slices) {
+                if (z == (zz[k] & 0xFFFF)) s_lo[k] = v;
+                if (z == (zz[k] >> 16)) s_hi[k] = v;
+            }
+        }
+    }
+
+    // planes are [field][ncol]
+    __device__ __forceinline__ void write(const ProductParams& pp, int field, int64_t col, int64_t ncol, float x,
+                                          float y) const
+    {
+        const size_t o = (size_t)field * (size_t)ncol + (size_t)col;
+        const float qnan = __uint_as_float(kCanonNaN);
+        if (pp.cmax_on) pp.cmax_out[o] = cmax;
+        if (pp.cmin_on) pp.cmin_out[o] = cmin;
+        if (pp.cmean_on) {
+            // _divide_by_count: true_divide(float32 sum, intp count) evaluates in float64, stored as float32
+            pp.cmean_out[o] = (float)__ddiv_rn((double)msum, (double)mcnt);
+        }
+#pragma unroll
+        for (int k = 0; k < RG_MAX_SLICES; ++k) {
+            if (k < pp.n_slices) {
+                const SliceParams& s = pp.slices[k];
+                if (s.kind == RG_PROD_BEAM) {
+                    const double tz = beam_target_z(s, x, y);
+                    const double zf = __ddiv_rn(__dsub_rn(tz, pp.z_min), pp.z_step);
+                    if (s.mode == 1) {
+                        const double zi = rint(zf);
+                        const bool ok = zi >= 0.0 && zi < (double)pp.nz_full;
+                        reinterpret_cast<float*>(s.out)[o] = ok ? s_lo[k] : qnan;       // products.py:263-272
+                    } else {
+                        const double w_hi = __dsub_rn(zf, floor(zf));                      // products.py:287-288
+                        const double w_lo = __dsub_rn(1.0, w_hi);
+                        double r = __dadd_rn(__dmul_rn(w_lo, (double)s_lo[k]), __dmul_rn(w_hi, (double)s_hi[k]));
+                        if (tz < pp.z_min || tz > pp.z_max) r = (double)qnan;              // products.py:306-309
+                        reinterpret_cast<double*>(s.out)[o] = r;
+                    }
+                } else if (s.mode == RG_BLEND_PICK) {
+                    reinterpret_cast<float*>(s.out)[o] = s_lo[k];
+                } else if (s.mode == RG_BLEND_F32) {
+                    reinterpret_cast<float*>(s.out)[o] =
+                        __fadd_rn(__fmul_rn((float)s.w_lo, s_lo[k]), __fmul_rn((float)s.w_hi, s_hi[k]));
+                } else {
+                    const double r = __dadd_rn(__dmul_rn(s.w_lo, (double)s_lo[k]), __dmul_rn(s.w_hi, (double)s_hi[k]));
+                    if (s.mode == RG_BLEND_F64_OUT64) reinterpret_cast<double*>(s.out)[o] = r;
+                    else reinterpret_cast<float*>(s.out)[o] = (float)r;
+                }
+            }
+        }
+    }
+};
+
+// Stand-alone products over existing grids: one thread per (column, field), coalesced along x.
+struct ProductsKernelParams {
+    const float* grids[RG_MAX_FIELDS];
+    int64_t ncol;
+    int32_t nx, n_levels, z_begin, n_fields;
+    ProductParams prod;
+};
+
+__global__ void __launch_bounds__(256) products_kernel(const __grid_constant__ ProductsKernelParams p)
+{
+    const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int field = blockIdx.y;
+    if (col >= p.ncol) return;
+    const float x = __ldg(p.prod.x_ax + (int)(col % p.nx));
+    const float y = __ldg(p.prod.y_ax + (int)(col / p.nx));
+    ColumnState st;
+    st.init(p.prod, x, y);
+    const float* __restrict__ grid = p.grids[field];
+    for (int lz = 0; lz < p.n_levels; ++lz) {
+        const float v = __ldcs(grid + (size_t)lz * (size_t)p.ncol + (size_t)col);
+        st.update(p.prod, p.z_begin + lz, v);
+    }
+    st.write(p.prod, field, col, p.ncol, x, y);
+}
+
+int launch_products(Context* ctx, const rg_grid_spec& grid, int n_fields, const float* const* grids_dev,
+                    const ProductParams& prod)
+{
+    ProductsKernelParams kp{};
+    for (int f = 0; f < n_fields; ++f) kp.grids[f] = grids_dev[f];
+    kp.ncol = (int64_t)grid.ny * grid.nx;
+    kp.nx = grid.nx;
+    kp.n_levels = grid.z_end - grid.z_begin;
+    kp.z_begin = grid.z_begin;
+    kp.n_fields = n_fields;
+    kp.prod = prod;
+    if (kp.ncol == 0 || n_fields == 0) return RG_OK;
+    dim3 blocks((unsigned)((kp.ncol + 255) / 256), (unsigned)n_fields);
+    products_kernel<<<blocks, 256, 0, ctx->stream>>>(kp);
+    ctx->launches++;
+    RG_CUDA(cudaGetLastError());
+    return RG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K5  fast path: column-tile CSR gather, W lanes per column, products in the epilogue
+// ------------------------------------------------------------------------------------------------------
+template <int FP>
+__device__ __forceinline__ void load_record(const float* __restrict__ rec, uint32_t gate, float (&v)[FP])
+{
+    if constexpr (FP == 1) {
+        v[0] = __ldg(rec + gate);
+    } else if constexpr (FP == 2) {
+        const float2 t = __ldg(reinterpret_cast<const float2*>(rec) + gate);
+        v[0] = t.x; v[1] = t.y;
+    } else if constexpr (FP == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(rec) + gate);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+        const float4* q = reinterpret_cast<const float4*>(rec) + 2 * (size_t)gate;
+        const float4 a = __ldg(q);
+        const float4 b = __ldg(q + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+}
+
+template <int F, int FP>
+__device__ __forceinline__ void accumulate(float w, const float (&v)[FP], float (&swv)[F], float (&sw)[F])
+{
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+        const bool m = __float_as_uint(v[f]) == kMaskedBits;   // interpolate.py:78-79
+        const float we = m ? 0.f : w;
+        const float vv = m ? 0.f : v[f];
+        sw[f] = __fadd_rn(sw[f], we);
+        swv[f] = fmaf(we, vv, swv[f]);
+    }
+}
+
+// Sum pairs [p, e) with stride `step`, four pairs (and their gathers) in flight per lane.
+template <int F, int FP>
+__device__ __forceinline__ void gather_run(const uint2* __restrict__ pairs, const float* __restrict__ rec,
+                                           uint32_t p, uint32_t e, uint32_t step, float (&swv)[F], float (&sw)[F])
+{
+    while (p < e && e - p > 3 * step) {
+        const uint2 a0 = __ldcs(pairs + p);
+        const uint2 a1 = __ldcs(pairs + p + step);
+        const uint2 a2 = __ldcs(pairs + p + 2 * step);
+        const uint2 a3 = __ldcs(pairs + p + 3 * step);
+        float v0[FP], v1[FP], v2[FP], v3[FP];
+        load_record<FP>(rec, a0.x, v0);
+        load_record<FP>(rec, a1.x, v1);
+        load_record<FP>(rec, a2.x, v2);
+        load_record<FP>(rec, a3.x, v3);
+        accumulate<F, FP>(__uint_as_float(a0.y), v0, swv, sw);
+        accumulate<F, FP>(__uint_as_float(a1.y), v1, swv, sw);
+        accumulate<F, FP>(__uint_as_float(a2.y), v2, swv, sw);
+        accumulate<F, FP>(__uint_as_float(a3.y), v3, swv, sw);
+        p += 4 * step;
+    }
+    while (p < e) {
+        const uint2 a0 = __ldcs(pairs + p);
+        float v0[FP];
+        load_record<FP>(rec, a0.x, v0);
+        accumulate<F, FP>(__uint_as_float(a0.y), v0, swv, sw);
+        p += step;
+    }
+}
+
+template <int F, int W, bool PROD>
+__global__ void __launch_bounds__(kApplyThreads) apply_columns_kernel(const __grid_constant__ ApplyParams p)
+{
+    constexpr int FP = F == 1 ? 1 : F == 2 ? 2 : F <= 4 ? 4 : 8;
+    static_assert(W >= F || W == 32, "one lane per field in the epilogue");
+    constexpr unsigned kFull = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    const int gl = threadIdx.x & (W - 1);                      // lane within the column group
+    const int64_t col = (int64_t)blockIdx.x * (kApplyThreads / W) + threadIdx.x / W;
+    const bool col_ok = col < p.ncol;
+    const bool owner = col_ok && gl < F;                       // lane gl finishes field gl
+
+    const uint32_t* __restrict__ indptr = p.indptr;
+    const uint2* __restrict__ pairs = p.pairs;
+    const float* __restrict__ rec = p.records;
+
+    float x = 0.f, y = 0.f;
+    ColumnState st;
+    if constexpr (PROD) {
+        if (owner) {
+            x = __ldg(p.prod.x_ax + (int)(col % p.nx));
+            y = __ldg(p.prod.y_ax + (int)(col / p.nx));
+        }
+        st.init(p.prod, x, y);
+    }
+
+    uint32_t s_next = 0, e_next = 0;
+    if (col_ok && p.lz_first < p.lz_last) {
+        const size_t row = (size_t)p.lz_first * (size_t)p.ncol + (size_t)col;
+        s_next = __ldg(indptr + row);
+        e_next = __ldg(indptr + row + 1);
+    }
+
+    for (int lz = p.lz_first; lz < p.lz_last; ++lz) {
+        const uint32_t s = s_next, e = e_next;
+        const size_t row = (size_t)lz * (size_t)p.ncol + (size_t)col;
+        if (col_ok && lz + 1 < p.lz_last) {                    // prefetch the next level's row bounds
+            s_next = __ldg(indptr + row + (size_t)p.ncol);
+            e_next = __ldg(indptr + row + (size_t)p.ncol + 1);
+        }
+
+        float swv[F], sw[F];
+#pragma unroll
+        for (int f = 0; f < F; ++f) { swv[f] = 0.f; sw[f] = 0.f; }
+
+        const uint32_t len = e - s;
+        bool heavy_mine = len > kHeavyRow;
+        if constexpr (W < 32) {
+            // Rows far longer than the group is wide (the voxels next to the radar see the first gates
+            // of every ray) are summed by the whole warp, then handed back to the owning group.
+            unsigned heavy = __ballot_sync(kFull, heavy_mine && gl == 0);
+            while (heavy) {
+                const int src = __ffs(heavy) - 1;
+                heavy &= heavy - 1;
+                const uint32_t hs = __shfl_sync(kFull, s, src);
+                const uint32_t he = __shfl_sync(kFull, e, src);
+                float hwv[F], hw[F];
+#pragma unroll
+                for (int f = 0; f < F; ++f) { hwv[f] = 0.f; hw[f] = 0.f; }
+                gather_run<F, FP>(pairs, rec, hs + lane, he, 32, hwv, hw);
+#pragma unroll
+                for (int f = 0; f < F; ++f) {
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) {
+                        hwv[f] += __shfl_xor_sync(kFull, hwv[f], off);
+                        hw[f] += __shfl_xor_sync(kFull, hw[f], off);
+                    }
+                }
+                if (lane == src) {                              // group leader keeps the row total
+#pragma unroll
+                    for (int f = 0; f < F; ++f) { swv[f] = hwv[f]; sw[f] = hw[f]; }
+                }
+            }
+        } else {
+            heavy_mine = false;
+        }
+
+        if (!heavy_mine) gather_run<F, FP>(pairs, rec, s + gl, e, W, swv, sw);
+
+        // butterfly inside the group: afterwards every lane of the group holds the row sums
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+#pragma unroll
+            for (int off = W / 2; off >= 1; off >>= 1) {
+                swv[f] += __shfl_xor_sync(kFull, swv[f], off);
+                sw[f] += __shfl_xor_sync(kFull, sw[f], off);
+            }
+        }
+
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int f = 0; f < F; ++f)
+            if (gl == f) { a = swv[f]; b = sw[f]; }
+
+        if (owner) {
+            const float v = b > 0.f ? __fdiv_rn(a, b) : p.fill;            // interpolate.py:99-102
+            float* out = p.grid_out[gl];
+            if (out != nullptr) __stcs(out + row, v);
+            if constexpr (PROD) st.update(p.prod, p.z_begin + lz, v);
+        }
+    }
+
+    if constexpr (PROD) {
+        if (owner) st.write(p.prod, gl, col, p.ncol, x, y);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K5  reference-order path: reproduces np.add.reduceat's summation order, so that on the reference's own
+//     table (KD-tree row order) the grid is bit-identical to interpolate.py's.  One thread per row.
+//     reduceat(seg) = a[0] + pairwise_sum(a[1:])   with NumPy's pairwise_sum: < 8 elements sequential,
+//     <= 128 eight interleaved accumulators, otherwise split at (n/2 rounded down to a multiple of 8).
+// ------------------------------------------------------------------------------------------------------
+template <int FP>
+struct RowTerms {
+    const uint2* pairs;
+    const float* rec;
+    int field;
+    bool weights_only;
+    __device__ __forceinline__ float at(uint32_t i) const
+    {
+        const uint2 pr = __ldg(pairs + i);
+        const float v = __ldg(rec + (size_t)pr.x * FP + field);
+        const bool m = __float_as_uint(v) == kMaskedBits;
+        const float we = m ? 0.f : __uint_as_float(pr.y);
+        if (weights_only) return we;
+        return __fmul_rn(we, m ? 0.f : v);                                  // interpolate.py:82
+    }
+};
+
+template <int FP>
+__device__ float pairwise_leaf(const RowTerms<FP>& t, uint32_t off, uint32_t n)
+{
+    if (n < 8) {
+        float res = 0.f;
+        for (uint32_t i = 0; i < n; ++i) res = __fadd_rn(res, t.at(off + i));
+        return res;
+    }
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = t.at(off + j);
+    uint32_t i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], t.at(off + i + j));
+    }
+    float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                          __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __fadd_rn(res, t.at(off + i));
+    return res;
+}
+
+template <int FP>
+__device__ float pairwise_sum(const RowTerms<FP>& t, uint32_t off, uint32_t n)
+{
+    if (n <= 128) return pairwise_leaf<FP>(t, off, n);
+    // explicit post-order walk of NumPy's recursion
+    struct Frame { uint32_t off, n; int stage; float left; };
+    Frame st[40];
+    int sp = 0;
+    st[0] = {off, n, 0, 0.f};
+    float ret = 0.f;
+    while (sp >= 0) {
+        Frame& f = st[sp];
+        if (f.n <= 128) {
+            ret = pairwise_leaf<FP>(t, f.off, f.n);
+            --sp;
+            continue;
+        }
+        uint32_t n2 = f.n / 2;
+        n2 -= n2 % 8;
+        if (f.stage == 0) {
+            f.stage = 1;
+            st[sp + 1] = {f.off, n2, 0, 0.f};
+            ++sp;
+        } else if (f.stage == 1) {
+            f.left = ret;
+            f.stage = 2;
+            st[sp + 1] = {f.off + n2, f.n - n2, 0, 0.f};
+            ++sp;
+        } else {
+            ret = __fadd_rn(f.left, ret);
+            --sp;
+        }
+    }
+    return ret;
+}
+
+template <int FP>
+__global__ void __launch_bounds__(128) apply_reference_order_kernel(const __grid_constant__ ApplyParams p, int64_t n_rows)
+{
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    const uint32_t s = __ldg(p.indptr + row), e = __ldg(p.indptr + row + 1);
+    for (int f = 0; f < p.n_fields; ++f) {
+        float* out = p.grid_out[f];
+        if (out == nullptr) continue;
+        float v = p.fill;
+        if (e > s) {
+            RowTerms<FP> t{p.pairs, p.records, f, false};
+            float swv = t.at(s);
+            if (e - s > 1) swv = __fadd_rn(swv, pairwise_sum<FP>(t, s + 1, e - s - 1));
+            t.weights_only = true;
+            float sw = t.at(s);
+            if (e - s > 1) sw = __fadd_rn(sw, pairwise_sum<FP>(t, s + 1, e - s - 1));
+            if (sw > 0.f) v = __fdiv_rn(swv, sw);
+        }
+        out[row] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// dispatch
+// ------------------------------------------------------------------------------------------------------
+template <int F, int W>
+static void launch_columns(Context* ctx, const ApplyParams& p)
+{
+    const int cols_per_cta = kApplyThreads / W;
+    const unsigned blocks = (unsigned)((p.ncol + cols_per_cta - 1) / cols_per_cta);
+    if (p.prod.any) apply_columns_kernel<F, W, true><<<blocks, kApplyThreads, 0, ctx->stream>>>(p);
+    else apply_columns_kernel<F, W, false><<<blocks, kApplyThreads, 0, ctx->stream>>>(p);
+}
+
+template <int F>
+static int launch_columns_w(Context* ctx, const ApplyParams& p, int W)
+{
+    if constexpr (F <= 4) {
+        if (W == 4) { launch_columns<F, 4>(ctx, p); return RG_OK; }
+    }
+    if (W <= 8) launch_columns<F, 8>(ctx, p);
+    else if (W == 16) launch_columns<F, 16>(ctx, p);
+    else launch_columns<F, 32>(ctx, p);
+    return RG_OK;
+}
+
+static int pick_group_width(const Context* ctx, const Geometry* g, int n_fields)
+{
+    int W = (int)ctx->group_width;
+    if (W == 0) {
+        const int64_t nonempty = g->info.n_rows - g->info.n_empty_rows;
+        const double avg = nonempty > 0 ? (double)g->info.n_pairs / (double)nonempty : 0.0;
+        W = avg < 6.0 ? 4 : avg < 96.0 ? 8 : avg < 400.0 ? 16 : 32;
+    }
+    if (W != 4 && W != 8 && W != 16 && W != 32) W = 8;
+    if (W < 8 && n_fields > 4) W = 8;
+    return W;
+}
+
+int launch_apply(Context* ctx, const Geometry* g, const ApplyParams& p, bool reference_order)
+{
+    if (g->n_rows == 0) return RG_OK;
+    if (reference_order) {
+        const unsigned blocks = (unsigned)((g->n_rows + 127) / 128);
+        switch (records_width(p.n_fields)) {
+            case 1: apply_reference_order_kernel<1><<<blocks, 128, 0, ctx->stream>>>(p, g->n_rows); break;
+            case 2: apply_reference_order_kernel<2><<<blocks, 128, 0, ctx->stream>>>(p, g->n_rows); break;
+            case 4: apply_reference_order_kernel<4><<<blocks, 128, 0, ctx->stream>>>(p, g->n_rows); break;
+            default: apply_reference_order_kernel<8><<<blocks, 128, 0, ctx->stream>>>(p, g->n_rows); break;
+        }
+        ctx->launches++;
+        RG_CUDA(cudaGetLastError());
+        return RG_OK;
+    }
+    const int W = pick_group_width(ctx, g, p.n_fields);
+    timer_begin(ctx, kTimerApply);
+    switch (p.n_fields) {
+        case 1: launch_columns_w<1>(ctx, p, W); break;
+        case 2: launch_columns_w<2>(ctx, p, W); break;
+        case 3: launch_columns_w<3>(ctx, p, W); break;
+        case 4: launch_columns_w<4>(ctx, p, W); break;
+        case 5: launch_columns_w<5>(ctx, p, W); break;
+        case 6: launch_columns_w<6>(ctx, p, W); break;
+        case 7: launch_columns_w<7>(ctx, p, W); break;
+        case 8: launch_columns_w<8>(ctx, p, W); break;
+        default: return fail(RG_ERR_INVALID, "n_fields must be 1..8");
+    }
+    timer_end(ctx, kTimerApply);
+    ctx->launches++;
+    RG_CUDA(cudaGetLastError());
+    return RG_OK;
+}
+
+}  // namespace rg

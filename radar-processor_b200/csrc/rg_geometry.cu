@@ -1,0 +1,601 @@
+// K1-K3: the per-voxel radius-of-influence neighbour table, built on the GPU.
+//
+// Reference being replaced: src/radar_grid/compute.py:18-103 (_process_single_level) and :106-284
+// (compute_grid_geometry).  There, every z-level worker rebuilds a cKDTree over the TOA-valid gates and a
+// Python loop ball-queries it voxel by voxel; the tree is only a candidate generator, the neighbour set is
+//     { gate : ((dx*dx + dy*dy) + dz*dz) < r*r },   r = max(min_radius, sqrt((x*x + y*y) + z*z) * beam_factor)
+// evaluated in float64 on float32-valued coordinates (compute.py:46-47, 69-74).  Here:
+//   K1  counting-sort binning of the gates into a uniform cell grid (deterministic: gate id order inside a cell)
+//   K2  one warp per voxel scans the cell rows its sphere touches (x-extent clipped per row) and counts the
+//       gates that pass the same float64 test, with every operation individually rounded (no FMA contraction)
+//   --  exclusive scan of the counts -> indptr
+//   K3  the same scan again, writing {gate id, float32 weight} pairs (compute.py:82-87)
+// The cell scan is a superset generator exactly like the KD-tree is, so the sets are identical.
+
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "rg_internal.cuh"
+
+namespace rg {
+
+namespace {
+
+constexpr int kScanTile = 4096;           // elements per CTA in the scan kernels (1024 threads x 4)
+constexpr uint32_t kLongRun = 24;         // candidate runs at least this long are scanned by the whole warp
+constexpr int64_t kMaxCells = 48ll << 20;
+
+struct CellGrid {
+    double ox, oy, oz, cell, inv_cell;
+    int32_t ncx, ncy, ncz;
+};
+
+struct BinParams {
+    const float* gx;
+    const float* gy;
+    const float* gz;
+    int64_t n_gates;
+    float radar_alt_f32, toa_f32;
+    CellGrid cg;
+    uint32_t* cell_of;                    // [n_gates]  cell id or kInvalidCell
+    uint32_t* cell_count;                 // [ncell]
+    unsigned long long* n_nonfinite;
+};
+
+__device__ __forceinline__ int cell_coord(double v, double origin, double inv_cell)
+{
+    // monotone in v; clamped so that far-away gates cannot overflow the int conversion
+    const double f = floor(__dmul_rn(__dsub_rn(v, origin), inv_cell));
+    return (int)fmin(fmax(f, -2.0), 2147483000.0);
+}
+
+// K1a: TOA cull (compute.py:182,193: float32 subtraction, float32 compare) + cell id + histogram
+__global__ void __launch_bounds__(256) bin_count_kernel(const __grid_constant__ BinParams p)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= p.n_gates) return;
+    const float x = __ldg(p.gx + g), y = __ldg(p.gy + g);
+    const float zr = __fsub_rn(__ldg(p.gz + g), p.radar_alt_f32);
+    uint32_t cell = kInvalidCell;
+    if (zr <= p.toa_f32) {
+        if (!(isfinite(x) && isfinite(y) && isfinite(zr))) {
+            atomicAdd(p.n_nonfinite, 1ull);           // the reference's cKDTree refuses non-finite data
+        } else {
+            const int cx = cell_coord((double)x, p.cg.ox, p.cg.inv_cell);
+            const int cy = cell_coord((double)y, p.cg.oy, p.cg.inv_cell);
+            const int cz = cell_coord((double)zr, p.cg.oz, p.cg.inv_cell);
+            if (cx >= 0 && cx < p.cg.ncx && cy >= 0 && cy < p.cg.ncy && cz >= 0 && cz < p.cg.ncz) {
+                cell = (uint32_t)(((int64_t)cz * p.cg.ncy + cy) * p.cg.ncx + cx);
+                atomicAdd(p.cell_count + cell, 1u);
+            }
+        }
+    }
+    p.cell_of[g] = cell;
+}
+
+// K1c: unordered scatter of gate ids into their cell's range
+__global__ void __launch_bounds__(256) bin_scatter_kernel(const uint32_t* __restrict__ cell_of, int64_t n_gates,
+                                                          const uint32_t* __restrict__ cell_start,
+                                                          uint32_t* __restrict__ cell_fill, uint32_t* __restrict__ slot_ids)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_gates) return;
+    const uint32_t c = cell_of[g];
+    if (c == kInvalidCell) return;
+    const uint32_t pos = cell_start[c] + atomicAdd(cell_fill + c, 1u);
+    slot_ids[pos] = (uint32_t)g;
+}
+
+// K1d: make the order inside every cell deterministic (ascending gate id) and gather the coordinates
+__global__ void __launch_bounds__(256) bin_rank_kernel(const uint32_t* __restrict__ slot_ids, int64_t n_binned,
+                                                       const uint32_t* __restrict__ cell_of,
+                                                       const uint32_t* __restrict__ cell_start,
+                                                       const float* __restrict__ gx, const float* __restrict__ gy,
+                                                       const float* __restrict__ gz, float radar_alt_f32,
+                                                       float4* __restrict__ sorted)
+{
+    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_binned) return;
+    const uint32_t id = slot_ids[slot];
+    const uint32_t c = cell_of[id];
+    const uint32_t s = cell_start[c], e = cell_start[c + 1];
+    uint32_t rank = 0;
+    for (uint32_t j = s; j < e; ++j) rank += __ldg(slot_ids + j) < id ? 1u : 0u;
+    sorted[s + rank] = make_float4(__ldg(gx + id), __ldg(gy + id), __fsub_rn(__ldg(gz + id), radar_alt_f32),
+                                   __uint_as_float(id));
+}
+
+// ---- exclusive scan of uint32 counts (64-bit total) ---------------------------------------------------
+__device__ __forceinline__ unsigned long long block_reduce_u64(unsigned long long v, unsigned long long* smem)
+{
+    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, off);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) smem[w] = v;
+    __syncthreads();
+    unsigned long long t = (threadIdx.x < (blockDim.x >> 5)) ? smem[threadIdx.x] : 0ull;
+    if (w == 0) {
+        for (int off = 16; off >= 1; off >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, off);
+        if (l == 0) smem[0] = t;
+    }
+    __syncthreads();
+    t = smem[0];
+    __syncthreads();
+    return t;
+}
+
+__global__ void __launch_bounds__(1024) scan_tile_sums_kernel(const uint32_t* __restrict__ in, int64_t n,
+                                                              unsigned long long* __restrict__ tile_sums)
+{
+    __shared__ unsigned long long smem[32];
+    const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * 4;
+    unsigned long long v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (base + k < n) v += in[base + k];
+    const unsigned long long t = block_reduce_u64(v, smem);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = t;
+}
+
+// single CTA: exclusive scan of the tile sums in place, grand total to *total
+__global__ void __launch_bounds__(1024) scan_tile_offsets_kernel(unsigned long long* __restrict__ tile_sums, int64_t n_tiles,
+                                                                 unsigned long long* __restrict__ total)
+{
+    __shared__ unsigned long long warp_tot[32];
+    __shared__ unsigned long long carry, chunk_total;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    for (int64_t base = 0; base < n_tiles; base += 1024) {
+        const int64_t i = base + threadIdx.x;
+        const unsigned long long v = i < n_tiles ? tile_sums[i] : 0ull;
+        unsigned long long incl = v;
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+            if (l >= off) incl += t;
+        }
+        if (l == 31) warp_tot[w] = incl;
+        __syncthreads();
+        if (w == 0) {
+            const unsigned long long t = warp_tot[l];
+            unsigned long long ti = t;
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, ti, off);
+                if (l >= off) ti += u;
+            }
+            warp_tot[l] = ti - t;          // exclusive prefix of the warp totals
+            if (l == 31) chunk_total = ti;
+        }
+        __syncthreads();
+        if (i < n_tiles) tile_sums[i] = carry + warp_tot[w] + (incl - v);
+        __syncthreads();
+        if (threadIdx.x == 0) carry += chunk_total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void __launch_bounds__(1024) scan_apply_kernel(const uint32_t* __restrict__ in, int64_t n,
+                                                          const unsigned long long* __restrict__ tile_offsets,
+                                                          uint32_t* __restrict__ out)
+{
+    __shared__ uint32_t warp_tot[32];
+    const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * 4;
+    uint32_t v[4];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        v[k] = base + k < n ? in[base + k] : 0u;
+        mine += v[k];
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    uint32_t incl = mine;
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+        if (l >= off) incl += t;
+    }
+    if (l == 31) warp_tot[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        const uint32_t t = warp_tot[l];
+        uint32_t ti = t;
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, ti, off);
+            if (l >= off) ti += u;
+        }
+        warp_tot[l] = ti - t;
+    }
+    __syncthreads();
+    uint32_t run = (uint32_t)tile_offsets[blockIdx.x] + warp_tot[w] + (incl - mine);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+    }
+}
+
+__global__ void scan_write_total_kernel(const unsigned long long* total, uint32_t* out_last)
+{
+    *out_last = (uint32_t)(*total);
+}
+
+// out[0..n] = exclusive scan of in[0..n-1]; *total_host = sum.  `tmp` must hold ceil(n/4096)+1 u64.
+int exclusive_scan_u32(Context* ctx, const uint32_t* in, uint32_t* out, int64_t n, unsigned long long* tmp,
+                       uint64_t* total_host)
+{
+    const int64_t n_tiles = (n + kScanTile - 1) / kScanTile;
+    unsigned long long* total_dev = tmp + n_tiles;
+    if (n_tiles > 0) {
+        scan_tile_sums_kernel<<<(unsigned)n_tiles, 1024, 0, ctx->stream>>>(in, n, tmp);
+        ctx->launches++;
+    }
+    scan_tile_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(tmp, n_tiles, total_dev);
+    ctx->launches++;
+    if (n_tiles > 0) {
+        scan_apply_kernel<<<(unsigned)n_tiles, 1024, 0, ctx->stream>>>(in, n, tmp, out);
+        ctx->launches++;
+    }
+    scan_write_total_kernel<<<1, 1, 0, ctx->stream>>>(total_dev, out + n);
+    ctx->launches++;
+    RG_CUDA(cudaGetLastError());
+    unsigned long long t = 0;
+    RG_CUDA(cudaMemcpyAsync(&t, total_dev, sizeof(t), cudaMemcpyDeviceToHost, ctx->stream));
+    RG_CUDA(cudaStreamSynchronize(ctx->stream));
+    *total_host = t;
+    return RG_OK;
+}
+
+// ---- K2 / K3: warp-per-voxel neighbour search -----------------------------------------------------------
+struct NeighbourParams {
+    const float4* sorted;                 // binned gates {x, y, z - radar_alt, id bits}
+    const uint32_t* cell_start;
+    CellGrid cg;
+    const float* x_ax;
+    const float* y_ax;
+    const float* z_ax;
+    int32_t nx, ny, z_begin;
+    int64_t ncol, n_rows;
+    double min_radius, beam_factor;
+    int32_t weighting;
+    uint32_t* counts;                     // K2 output
+    const uint32_t* indptr;               // K3 input
+    uint2* pairs;                         // K3 output
+    unsigned long long* n_candidates;
+};
+
+__device__ __forceinline__ float neighbour_weight(int weighting, double d2, double r2)
+{
+    if (weighting == RG_W_BARNES2)        // compute.py:83
+        return __double2float_rn(__dadd_rn(exp(__ddiv_rn(-d2, __ddiv_rn(r2, 4.0))), 1e-5));
+    if (weighting == RG_W_CRESSMAN)       // compute.py:85
+        return __double2float_rn(__ddiv_rn(__dsub_rn(r2, d2), __dadd_rn(r2, d2)));
+    return 1.0f;                          // compute.py:87 ('nearest' = every gate in the ROI, weight 1)
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) neighbour_kernel(const __grid_constant__ NeighbourParams p)
+{
+    constexpr unsigned kFull = 0xFFFFFFFFu;
+    __shared__ unsigned long long cta_candidates;
+    if (threadIdx.x == 0) cta_candidates = 0;
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    unsigned long long tested = 0;
+
+    if (row < p.n_rows) {
+        const int lz = (int)(row / p.ncol);
+        const int64_t c = row - (int64_t)lz * p.ncol;
+        const int iy = (int)(c / p.nx), ix = (int)(c - (int64_t)iy * p.nx);
+        // compute.py:43,189-190: float32 axis values widened to float64
+        const double vx = (double)__ldg(p.x_ax + ix);
+        const double vy = (double)__ldg(p.y_ax + iy);
+        const double vz = (double)__ldg(p.z_ax + p.z_begin + lz);
+        // compute.py:46-47
+        const double dist = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)), __dmul_rn(vz, vz)));
+        const double r = fmax(p.min_radius, __dmul_rn(dist, p.beam_factor));
+        const double r2 = __dmul_rn(r, r);
+        // conservative (padded) search radius for the cell scan; the exact test below decides membership
+        const double rp = r * (1.0 + 1e-9) + 1e-3;
+        const CellGrid& cg = p.cg;
+        const int czlo = max(0, min(cg.ncz - 1, cell_coord(vz - rp, cg.oz, cg.inv_cell)));
+        const int czhi = max(0, min(cg.ncz - 1, cell_coord(vz + rp, cg.oz, cg.inv_cell)));
+        const int cylo = max(0, min(cg.ncy - 1, cell_coord(vy - rp, cg.oy, cg.inv_cell)));
+        const int cyhi = max(0, min(cg.ncy - 1, cell_coord(vy + rp, cg.oy, cg.inv_cell)));
+        const int yspan = cyhi - cylo + 1;
+        const int n_scan = (czhi - czlo + 1) * yspan;
+
+        uint32_t found = 0;                               // warp-uniform running count
+        uint32_t out_base = 0;
+        if (FILL) out_base = __ldg(p.indptr + row);
+
+        auto test_candidate = [&](bool in, uint32_t k) {
+            bool keep = false;
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            double d2 = 0.0;
+            if (in) {
+                g = __ldg(p.sorted + k);
+                // compute.py:69-74, float64, each operation rounded on its own
+                const double dx = __dsub_rn((double)g.x, vx);
+                const double dy = __dsub_rn((double)g.y, vy);
+                const double dz = __dsub_rn((double)g.z, vz);
+                d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                keep = d2 < r2;
+            }
+            const unsigned km = __ballot_sync(kFull, keep);
+            if (FILL && keep) {
+                const uint32_t pos = out_base + found + __popc(km & lt_mask);
+                p.pairs[pos] = make_uint2(__float_as_uint(g.w), __float_as_uint(neighbour_weight(p.weighting, d2, r2)));
+            }
+            found += __popc(km);
+        };
+
+        for (int base = 0; base < n_scan; base += 32) {
+            const int i = base + lane;
+            uint32_t s = 0, e = 0;
+            if (i < n_scan) {
+                const int cz = czlo + i / yspan;
+                const int cy = cylo + i % yspan;
+                const double zlo = cg.oz + cz * cg.cell, ylo = cg.oy + cy * cg.cell;
+                const double dzm = fmax(0.0, fmax(zlo - vz, vz - (zlo + cg.cell)));
+                const double dym = fmax(0.0, fmax(ylo - vy, vy - (ylo + cg.cell)));
+                const double h2 = rp * rp - dzm * dzm - dym * dym;
+                if (h2 > 0.0) {
+                    const double hx = sqrt(h2) + 1e-3;
+                    const int cxlo = max(0, min(cg.ncx - 1, cell_coord(vx - hx, cg.ox, cg.inv_cell)));
+                    const int cxhi = max(0, min(cg.ncx - 1, cell_coord(vx + hx, cg.ox, cg.inv_cell)));
+                    const size_t rb = ((size_t)cz * cg.ncy + cy) * (size_t)cg.ncx;
+                    s = __ldg(p.cell_start + rb + cxlo);
+                    e = __ldg(p.cell_start + rb + cxhi + 1);
+                }
+            }
+            const uint32_t len = e - s;
+            tested += len;
+
+            // long candidate runs: all 32 lanes stride over the run (coalesced 16-byte loads)
+            unsigned longm = __ballot_sync(kFull, len >= kLongRun);
+            while (longm) {
+                const int src = __ffs(longm) - 1;
+                longm &= longm - 1;
+                const uint32_t hs = __shfl_sync(kFull, s, src);
+                const uint32_t he = __shfl_sync(kFull, e, src);
+                for (uint32_t k0 = hs; k0 < he; k0 += 32) test_candidate(k0 + lane < he, k0 + lane);
+            }
+            // short runs: every lane walks its own run, in lockstep
+            const uint32_t slen = len < kLongRun ? len : 0u;
+            const uint32_t smax = __reduce_max_sync(kFull, slen);
+            for (uint32_t j = 0; j < smax; ++j) test_candidate(j < slen, s + j);
+        }
+        if (!FILL && lane == 0) p.counts[row] = found;
+    }
+
+    if (!FILL) {
+        for (int off = 16; off >= 1; off >>= 1) tested += __shfl_xor_sync(kFull, tested, off);
+        if (lane == 0 && tested) atomicAdd(&cta_candidates, tested);
+        __syncthreads();
+        if (threadIdx.x == 0 && cta_candidates) atomicAdd(p.n_candidates, cta_candidates);
+    }
+}
+
+// ---- row statistics ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) row_stats_kernel(const uint32_t* __restrict__ indptr, int64_t n_rows,
+                                                        unsigned long long* __restrict__ n_empty,
+                                                        unsigned int* __restrict__ max_len)
+{
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t len = 0;
+    bool empty = false;
+    if (row < n_rows) {
+        len = indptr[row + 1] - indptr[row];
+        empty = len == 0;
+    }
+    const unsigned em = __ballot_sync(0xFFFFFFFFu, empty);
+    const uint32_t wmax = __reduce_max_sync(0xFFFFFFFFu, len);
+    if ((threadIdx.x & 31) == 0) {
+        if (em) atomicAdd(n_empty, (unsigned long long)__popc(em));
+        if (wmax) atomicMax(max_len, wmax);
+    }
+}
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)); }
+};
+
+}  // namespace
+
+void linspace_f32(double start, double stop, int num, float* out)
+{
+    // numpy.linspace(start, stop, num, dtype=float32): float64 arange * step + start, last = stop, then cast
+    if (num <= 0) return;
+    const int div = num - 1;
+    const double delta = stop - start;
+    if (div > 0) {
+        const double step = delta / div;
+        for (int i = 0; i < num; ++i) {
+            double y = (double)i;
+            if (step == 0.0) y = (y / div) * delta;
+            else y = y * step;
+            out[i] = (float)(y + start);
+        }
+        out[num - 1] = (float)stop;
+    } else {
+        out[0] = (float)(0.0 * delta + start);
+    }
+}
+
+int finalize_geometry_stats(Context* ctx, Geometry* g)
+{
+    DevBuf<unsigned long long> stat;
+    RG_CUDA(stat.alloc(2));
+    RG_CUDA(cudaMemsetAsync(stat.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    if (g->n_rows > 0) {
+        row_stats_kernel<<<(unsigned)((g->n_rows + 255) / 256), 256, 0, ctx->stream>>>(
+            g->indptr, g->n_rows, stat.p, reinterpret_cast<unsigned int*>(stat.p + 1));
+        ctx->launches++;
+        RG_CUDA(cudaGetLastError());
+    }
+    unsigned long long h[2] = {0, 0};
+    RG_CUDA(cudaMemcpyAsync(h, stat.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    RG_CUDA(cudaStreamSynchronize(ctx->stream));
+    g->info.n_empty_rows = (int64_t)h[0];
+    g->info.max_row_len = (int64_t)(h[1] & 0xFFFFFFFFull);
+    return RG_OK;
+}
+
+int build_geometry_device(Context* ctx, const float* gx, const float* gy, const float* gz, int64_t n_gates,
+                          double radar_altitude, double min_radius, double beam_factor, int weighting, double toa,
+                          Geometry* out)
+{
+    const rg_grid_spec& gs = out->grid;
+    const int n_levels = gs.z_end - gs.z_begin;
+    const int64_t ncol = (int64_t)gs.ny * gs.nx;
+    const int64_t n_rows = ncol * n_levels;
+
+    // host copies of the axes (tiny) to size the cell grid
+    std::vector<float> xa(gs.nx), ya(gs.ny), za(gs.nz);
+    linspace_f32(gs.x_min, gs.x_max, gs.nx, xa.data());
+    linspace_f32(gs.y_min, gs.y_max, gs.ny, ya.data());
+    linspace_f32(gs.z_min, gs.z_max, gs.nz, za.data());
+    auto lohi = [](const std::vector<float>& a, int b, int e, double& lo, double& hi) {
+        lo = 1e300; hi = -1e300;
+        for (int i = b; i < e; ++i) { lo = std::min(lo, (double)a[i]); hi = std::max(hi, (double)a[i]); }
+        if (b >= e) lo = hi = 0.0;
+    };
+    double xlo, xhi, ylo, yhi, zlo, zhi;
+    lohi(xa, 0, gs.nx, xlo, xhi);
+    lohi(ya, 0, gs.ny, ylo, yhi);
+    lohi(za, gs.z_begin, gs.z_end, zlo, zhi);
+    const double ax = std::max(fabs(xlo), fabs(xhi)), ay = std::max(fabs(ylo), fabs(yhi)), az = std::max(fabs(zlo), fabs(zhi));
+    const double rmax = std::max(min_radius, sqrt(ax * ax + ay * ay + az * az) * beam_factor);
+    const double pad = rmax * (1.0 + 1e-6) + 1.0;
+
+    CellGrid cg{};
+    cg.ox = xlo - pad; cg.oy = ylo - pad; cg.oz = zlo - pad;
+    const double ex = (xhi + pad) - cg.ox, ey = (yhi + pad) - cg.oy, ez = (zhi + pad) - cg.oz;
+    double cell = std::max(2.0 * min_radius, 1e-3);
+    cell = std::max(cell, std::max(ex, std::max(ey, ez)) / 2048.0);
+    for (;;) {
+        const double cells = (floor(ex / cell) + 1) * (floor(ey / cell) + 1) * (floor(ez / cell) + 1);
+        if (cells <= (double)kMaxCells) break;
+        cell *= 1.2;
+    }
+    cg.cell = cell;
+    cg.inv_cell = 1.0 / cell;
+    cg.ncx = (int)floor(ex / cell) + 1;
+    cg.ncy = (int)floor(ey / cell) + 1;
+    cg.ncz = (int)floor(ez / cell) + 1;
+    const int64_t ncell = (int64_t)cg.ncx * cg.ncy * cg.ncz;
+
+    cudaEvent_t ev0, ev1;
+    RG_CUDA(cudaEventCreate(&ev0));
+    RG_CUDA(cudaEventCreate(&ev1));
+    RG_CUDA(cudaEventRecord(ev0, ctx->stream));
+
+    // ---- K1 binning
+    DevBuf<uint32_t> cell_of, cell_count, cell_start, slot_ids;
+    DevBuf<float4> sorted;
+    DevBuf<unsigned long long> scan_tmp, counters;
+    const int64_t scan_len = std::max(ncell, n_rows);
+    RG_CUDA(cell_of.alloc((size_t)n_gates));
+    RG_CUDA(cell_count.alloc((size_t)ncell));
+    RG_CUDA(cell_start.alloc((size_t)ncell + 1));
+    RG_CUDA(scan_tmp.alloc((size_t)(scan_len / kScanTile + 4)));
+    RG_CUDA(counters.alloc(2));
+    RG_CUDA(cudaMemsetAsync(cell_count.p, 0, (size_t)ncell * sizeof(uint32_t), ctx->stream));
+    RG_CUDA(cudaMemsetAsync(counters.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
+
+    BinParams bp{};
+    bp.gx = gx; bp.gy = gy; bp.gz = gz; bp.n_gates = n_gates;
+    bp.radar_alt_f32 = (float)radar_altitude;     // compute.py:182: float32 array - Python float stays float32
+    bp.toa_f32 = (float)toa;                      // compute.py:193: compared in float32 (NEP 50 weak scalar)
+    bp.cg = cg; bp.cell_of = cell_of.p; bp.cell_count = cell_count.p; bp.n_nonfinite = counters.p;
+    if (n_gates > 0) {
+        bin_count_kernel<<<(unsigned)((n_gates + 255) / 256), 256, 0, ctx->stream>>>(bp);
+        ctx->launches++;
+        RG_CUDA(cudaGetLastError());
+    }
+    uint64_t n_binned = 0;
+    RG_TRY(exclusive_scan_u32(ctx, cell_count.p, cell_start.p, ncell, scan_tmp.p, &n_binned));
+    unsigned long long nonfinite = 0;
+    RG_CUDA(cudaMemcpy(&nonfinite, counters.p, sizeof(nonfinite), cudaMemcpyDeviceToHost));
+    if (nonfinite != 0) {
+        cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+        return fail(RG_ERR_INVALID, "data must be finite, check for nan or inf values (gate coordinates below toa)");
+    }
+    RG_CUDA(slot_ids.alloc((size_t)n_binned));
+    RG_CUDA(sorted.alloc((size_t)n_binned));
+    if (n_binned > 0) {
+        RG_CUDA(cudaMemsetAsync(cell_count.p, 0, (size_t)ncell * sizeof(uint32_t), ctx->stream));   // reuse as fill cursor
+        bin_scatter_kernel<<<(unsigned)((n_gates + 255) / 256), 256, 0, ctx->stream>>>(cell_of.p, n_gates, cell_start.p,
+                                                                                       cell_count.p, slot_ids.p);
+        bin_rank_kernel<<<(unsigned)((n_binned + 255) / 256), 256, 0, ctx->stream>>>(
+            slot_ids.p, (int64_t)n_binned, cell_of.p, cell_start.p, gx, gy, gz, bp.radar_alt_f32, sorted.p);
+        ctx->launches += 2;
+        RG_CUDA(cudaGetLastError());
+    }
+
+    // ---- axes on the device (kept by the geometry: the product epilogues need x/y)
+    RG_CUDA(cudaMalloc(&out->x_ax, std::max(1, gs.nx) * sizeof(float)));
+    RG_CUDA(cudaMalloc(&out->y_ax, std::max(1, gs.ny) * sizeof(float)));
+    RG_CUDA(cudaMalloc(&out->z_ax, std::max(1, gs.nz) * sizeof(float)));
+    RG_CUDA(cudaMemcpyAsync(out->x_ax, xa.data(), gs.nx * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    RG_CUDA(cudaMemcpyAsync(out->y_ax, ya.data(), gs.ny * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    RG_CUDA(cudaMemcpyAsync(out->z_ax, za.data(), gs.nz * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    RG_CUDA(cudaStreamSynchronize(ctx->stream));   // xa/ya/za are stack-owned
+
+    // ---- K2 count
+    DevBuf<uint32_t> counts;
+    RG_CUDA(counts.alloc((size_t)n_rows));
+    RG_CUDA(cudaMalloc(&out->indptr, ((size_t)n_rows + 1) * sizeof(uint32_t)));
+    NeighbourParams np{};
+    np.sorted = sorted.p; np.cell_start = cell_start.p; np.cg = cg;
+    np.x_ax = out->x_ax; np.y_ax = out->y_ax; np.z_ax = out->z_ax;
+    np.nx = gs.nx; np.ny = gs.ny; np.z_begin = gs.z_begin; np.ncol = ncol; np.n_rows = n_rows;
+    np.min_radius = min_radius; np.beam_factor = beam_factor; np.weighting = weighting;
+    np.counts = counts.p; np.n_candidates = counters.p + 1;
+    const unsigned nb = (unsigned)((n_rows + 7) / 8);
+    if (n_rows > 0) {
+        neighbour_kernel<false><<<nb, 256, 0, ctx->stream>>>(np);
+        ctx->launches++;
+        RG_CUDA(cudaGetLastError());
+    }
+    uint64_t n_pairs = 0;
+    RG_TRY(exclusive_scan_u32(ctx, counts.p, out->indptr, n_rows, scan_tmp.p, &n_pairs));
+    if (n_pairs >= 0xFFFFFFFFull) {
+        cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+        return fail(RG_ERR_UNSUPPORTED,
+                    "neighbour table of this slab exceeds 2^32-1 pairs; split the grid into thinner z-slabs (z_begin/z_end)");
+    }
+
+    // ---- K3 fill
+    RG_CUDA(cudaMalloc(&out->pairs, std::max<size_t>((size_t)n_pairs, 1) * sizeof(uint2)));
+    np.indptr = out->indptr; np.pairs = out->pairs;
+    if (n_rows > 0 && n_pairs > 0) {
+        neighbour_kernel<true><<<nb, 256, 0, ctx->stream>>>(np);
+        ctx->launches++;
+        RG_CUDA(cudaGetLastError());
+    }
+    RG_CUDA(cudaEventRecord(ev1, ctx->stream));
+    RG_CUDA(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    RG_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    unsigned long long cand = 0;
+    RG_CUDA(cudaMemcpy(&cand, counters.p + 1, sizeof(cand), cudaMemcpyDeviceToHost));
+
+    out->n_rows = n_rows; out->n_pairs = (int64_t)n_pairs; out->n_gates = n_gates; out->ncol = ncol; out->n_levels = n_levels;
+    out->info.n_rows = n_rows; out->info.n_pairs = (int64_t)n_pairs; out->info.n_gates = n_gates;
+    out->info.n_gates_binned = (int64_t)n_binned; out->info.n_candidates = (int64_t)cand;
+    out->info.build_ms = ms; out->info.cell_size = cell; out->info.grid = gs;
+    out->info.device_bytes = (int64_t)(((size_t)n_rows + 1) * 4 + (size_t)n_pairs * 8);
+    return finalize_geometry_stats(ctx, out);
+}
+
+}  // namespace rg

@@ -1,0 +1,156 @@
+// Internal declarations shared by the translation units of libradargrid_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "radar_grid_b200.h"
+
+namespace rg {
+
+// ---- error plumbing ---------------------------------------------------------------------------------
+void set_error(const std::string& msg);
+int fail(int status, const std::string& msg);
+
+#define RG_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t rg_e_ = (expr);                                                                \
+        if (rg_e_ != cudaSuccess)                                                                  \
+            return ::rg::fail(rg_e_ == cudaErrorMemoryAllocation ? RG_ERR_NOMEM : RG_ERR_CUDA,     \
+                              std::string(#expr) + ": " + cudaGetErrorString(rg_e_));              \
+    } while (0)
+
+#define RG_TRY(expr)                          \
+    do {                                      \
+        int rg_s_ = (expr);                   \
+        if (rg_s_ != RG_OK) return rg_s_;     \
+    } while (0)
+
+// ---- constants --------------------------------------------------------------------------------------
+// A masked gate value is stored as this bit pattern inside the packed gate records (a NaN payload no
+// arithmetic produces); genuine NaNs are canonicalised to kCanonNaN by the pack kernel so that an
+// *unmasked* NaN still propagates exactly as in the reference (interpolate.py:78-82).
+constexpr uint32_t kMaskedBits = 0xFFFFFFFFu;
+constexpr uint32_t kCanonNaN = 0x7FC00000u;
+constexpr uint32_t kInvalidCell = 0xFFFFFFFFu;
+
+constexpr int kApplyThreads = 256;       // threads per CTA of the column-tile apply kernel
+constexpr uint32_t kHeavyRow = 512;      // rows longer than this are reduced by the whole warp
+
+// Device-resident neighbour table of one z-slab.
+struct Geometry {
+    int device = 0;
+    rg_grid_spec grid{};
+    int64_t n_rows = 0, n_pairs = 0, n_gates = 0, ncol = 0;
+    int32_t n_levels = 0;
+    uint32_t* indptr = nullptr;          // [n_rows + 1]
+    uint2* pairs = nullptr;              // [n_pairs] {gate id, float32 weight bits}
+    float* x_ax = nullptr;               // [nx]   float32 linspace axes (reference compute.py:184-186)
+    float* y_ax = nullptr;               // [ny]
+    float* z_ax = nullptr;               // [nz]   (full grid)
+    rg_geometry_info info{};
+};
+
+// Per-(device, stream) state: the stream and grow-only scratch buffers.
+struct Scratch {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+};
+
+// Optional per-kernel device timing (bench.py roofline): CUDA events recorded around the pack / apply launches.
+struct KernelTimer {
+    std::vector<cudaEvent_t> start, stop;
+};
+enum { kTimerPack = 0, kTimerApply = 1, kTimerCount = 2 };
+
+struct Context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int64_t launches = 0;
+    int64_t apply_variant = 0;           // 0 = auto
+    int64_t group_width = 0;             // 0 = auto
+    int sm_count = 148;
+    int64_t timing = 0;                  // record events around pack/apply launches
+    KernelTimer timers[kTimerCount];
+    Scratch records;                     // packed gate records
+    Scratch stage_in;                    // H2D staging of fields / masks / rule values
+    Scratch stage_out;                   // device-side outputs of a host-memspace call
+    Scratch misc;
+};
+
+int ensure(Context* ctx, Scratch& s, size_t bytes);
+void timer_begin(Context* ctx, int which);
+void timer_end(Context* ctx, int which);
+
+// ---- kernel-facing parameter blocks -----------------------------------------------------------------
+struct SliceParams {                      // one RG_PROD_LEVEL / RG_PROD_BEAM product
+    int32_t kind;                         // 0 = unused, RG_PROD_LEVEL, RG_PROD_BEAM
+    int32_t mode;                         // LEVEL: rg_blend_mode.  BEAM: 0 linear, 1 nearest
+    int32_t z_lo, z_hi;
+    int32_t curvature;
+    int32_t pad_;
+    double w_lo, w_hi;
+    double sin_e, cos_c, tan_e, ke_re, ke_re_sq;
+    void* out;
+};
+
+struct ProductParams {
+    int32_t any;                          // any product requested
+    int32_t cmax_on, cmax_z0, cmax_z1;
+    int32_t cmin_on, cmin_z0, cmin_z1;
+    int32_t cmean_on, cmean_z0, cmean_z1;
+    int32_t n_slices;
+    int32_t nz_full;
+    float* cmax_out;
+    float* cmin_out;
+    float* cmean_out;
+    double z_min, z_max, z_step;
+    const float* x_ax;
+    const float* y_ax;
+    SliceParams slices[RG_MAX_SLICES];
+};
+
+struct ApplyParams {
+    const uint32_t* indptr;
+    const uint2* pairs;
+    const float* records;                 // [n_gates][FP]
+    int64_t ncol;                         // ny*nx
+    int32_t nx, ny;
+    int32_t z_begin;                      // global index of local level 0
+    int32_t lz_first, lz_last;            // local levels [first, last) this launch walks
+    int32_t n_fields;
+    float fill;
+    float* grid_out[RG_MAX_FIELDS];
+    ProductParams prod;
+};
+
+struct PackParams {
+    int64_t n_gates;
+    int32_t n_fields;
+    int32_t n_rules;
+    uint32_t invalid_bits;
+    const float* fields[RG_MAX_FIELDS];
+    const uint8_t* masks[RG_MAX_FIELDS];
+    const float* rule_values[RG_MAX_RULES];
+    float rule_lo[RG_MAX_RULES], rule_hi[RG_MAX_RULES];
+    int32_t rule_use_lo[RG_MAX_RULES], rule_use_hi[RG_MAX_RULES];
+    uint32_t rule_bits[RG_MAX_RULES];
+    float* records;
+};
+
+// ---- launchers (defined in the .cu files) -----------------------------------------------------------
+int records_width(int n_fields);          // floats per packed gate record: 1, 2, 4 or 8
+int launch_pack(Context* ctx, const PackParams& p);
+int launch_apply(Context* ctx, const Geometry* g, const ApplyParams& p, bool reference_order);
+int launch_products(Context* ctx, const rg_grid_spec& grid, int n_fields, const float* const* grids_dev,
+                    const ProductParams& prod);
+int build_geometry_device(Context* ctx, const float* gx, const float* gy, const float* gz, int64_t n_gates,
+                          double radar_altitude, double min_radius, double beam_factor, int weighting,
+                          double toa, Geometry* out);
+int finalize_geometry_stats(Context* ctx, Geometry* g);
+void linspace_f32(double start, double stop, int num, float* out);
+
+}  // namespace rg

@@ -1,0 +1,456 @@
+"""
+Device-side engine: the thin host layer between the reference-shaped Python API and the C ABI.
+
+``DeviceGeometry`` owns a device-resident neighbour table (one z-slab); ``grid_fields`` runs one fused
+pass — gate-mask fusion + record packing (K4), CSR gather-weighted mean for up to 8 fields per index load
+(K5) and the COLMAX / CAPPI / PPI epilogue (K6) — on host (NumPy) or device (torch CUDA) buffers.
+
+The product classes below hold only the *host decisions* the reference makes in Python before touching
+the grid (which level, which weights, which dtype); they mirror the reference line by line so that the
+kernels receive exactly the scalars NumPy would have used.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import logging
+import warnings
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native as N
+
+logger = logging.getLogger(__name__)
+
+EARTH_RADIUS = 6371000.0
+EFFECTIVE_RADIUS_FACTOR = 4.0 / 3.0
+
+
+def _grid_spec(grid_shape, grid_limits, z_range=None) -> N.GridSpec:
+    nz, ny, nx = (int(v) for v in grid_shape)
+    z0, z1 = (0, nz) if z_range is None else (int(z_range[0]), int(z_range[1]))
+    (zmin, zmax), (ymin, ymax), (xmin, xmax) = grid_limits
+    return N.GridSpec(nz, ny, nx, z0, z1, 0, float(zmin), float(zmax), float(ymin), float(ymax),
+                      float(xmin), float(xmax))
+
+
+class DeviceGeometry:
+    """Device-resident CSR neighbour table of one z-slab (``rg_geometry``)."""
+
+    def __init__(self, handle, ctx: N.Context, grid_shape, grid_limits, z_range):
+        self._h = handle
+        self.ctx = ctx
+        self.grid_shape = tuple(int(v) for v in grid_shape)
+        self.grid_limits = grid_limits
+        self.z_range = (0, self.grid_shape[0]) if z_range is None else (int(z_range[0]), int(z_range[1]))
+        self._info = None
+
+    # -- constructors
+    @classmethod
+    def build(cls, gate_x, gate_y, gate_z, grid_shape, grid_limits, radar_altitude=0.0, min_radius=250.0,
+              beam_factor=0.01746, weighting="barnes2", toa=17000.0, z_range=None,
+              ctx: Optional[N.Context] = None) -> "DeviceGeometry":
+        """GPU build (K1-K3); replaces reference compute.py:106-284."""
+        if weighting not in N.RG_W:
+            raise ValueError(f"Unknown weighting function: {weighting}")
+        ctx = ctx or N.default_context()
+        spec = _grid_spec(grid_shape, grid_limits, z_range)
+        h = C.c_void_p()
+        if N.is_device_array(gate_x):
+            ptrs = [N.device_ptr(a) for a in (gate_x, gate_y, gate_z)]
+            n = int(gate_x.numel()) if hasattr(gate_x, "numel") else int(np.prod(gate_x.shape))
+            space = N.RG_DEVICE
+            keep = (gate_x, gate_y, gate_z)
+        else:
+            keep = tuple(np.ascontiguousarray(np.asarray(a).ravel(), dtype=np.float32) for a in (gate_x, gate_y, gate_z))
+            if not (keep[0].shape == keep[1].shape == keep[2].shape):
+                raise ValueError("gate_x, gate_y and gate_z must have the same length")
+            ptrs = [N.host_ptr(a) for a in keep]
+            n = keep[0].shape[0]
+            space = N.RG_HOST
+        N.check(N.lib().rg_geometry_build(ctx.handle, ptrs[0], ptrs[1], ptrs[2], n, space, C.byref(spec),
+                                          float(radar_altitude), float(min_radius), float(beam_factor),
+                                          N.RG_W[weighting], float(toa), C.byref(h)))
+        del keep
+        return cls(h, ctx, grid_shape, grid_limits, z_range)
+
+    @classmethod
+    def from_csr(cls, indptr, gate_indices, weights, grid_shape, grid_limits, n_gates: int, z_range=None,
+                 ctx: Optional[N.Context] = None) -> "DeviceGeometry":
+        """Upload an existing table (row order preserved), e.g. one built and saved by the reference."""
+        ctx = ctx or N.default_context()
+        spec = _grid_spec(grid_shape, grid_limits, z_range)
+        indptr = np.ascontiguousarray(indptr)
+        if indptr.dtype.itemsize == 8:
+            indptr = indptr.astype(np.int64, copy=False)
+            bits = 64
+        else:
+            indptr = indptr.astype(np.int32, copy=False)
+            bits = 32
+        n_rows = (spec.z_end - spec.z_begin) * spec.ny * spec.nx
+        if indptr.shape[0] != n_rows + 1:
+            raise ValueError(f"indptr has {indptr.shape[0]} entries, expected {n_rows + 1}")
+        idx = np.ascontiguousarray(gate_indices, dtype=np.int32)
+        w = np.ascontiguousarray(weights, dtype=np.float32)
+        if idx.shape[0] != w.shape[0] or idx.shape[0] != int(indptr[-1]):
+            raise ValueError("gate_indices / weights length must equal indptr[-1]")
+        h = C.c_void_p()
+        N.check(N.lib().rg_geometry_from_csr(ctx.handle, C.byref(spec), N.host_ptr(indptr), bits,
+                                             N.host_ptr(idx) if idx.size else None,
+                                             N.host_ptr(w) if w.size else None, int(n_gates), N.RG_HOST, C.byref(h)))
+        return cls(h, ctx, grid_shape, grid_limits, z_range)
+
+    # -- queries
+    @property
+    def info(self) -> dict:
+        if self._info is None:
+            gi = N.GeometryInfo()
+            N.check(N.lib().rg_geometry_get_info(self._h, C.byref(gi)))
+            self._info = {k: getattr(gi, k) for k, _ in N.GeometryInfo._fields_ if k != "grid"}
+        return self._info
+
+    @property
+    def n_pairs(self) -> int:
+        return int(self.info["n_pairs"])
+
+    @property
+    def n_rows(self) -> int:
+        return int(self.info["n_rows"])
+
+    @property
+    def n_gates(self) -> int:
+        return int(self.info["n_gates"])
+
+    @property
+    def slab_shape(self) -> Tuple[int, int, int]:
+        return (self.z_range[1] - self.z_range[0], self.grid_shape[1], self.grid_shape[2])
+
+    def export_csr(self, index_dtype=None):
+        """(indptr, gate_indices int32, weights float32) as NumPy arrays — the reference's GridGeometry arrays."""
+        n_rows, n_pairs = self.n_rows, self.n_pairs
+        if index_dtype is None:
+            index_dtype = np.int32 if n_pairs <= 0x7FFFFFFF else np.int64
+        indptr = np.empty(n_rows + 1, dtype=index_dtype)
+        idx = np.empty(n_pairs, dtype=np.int32)
+        w = np.empty(n_pairs, dtype=np.float32)
+        N.check(N.lib().rg_geometry_export_csr(self.ctx.handle, self._h, N.host_ptr(indptr), indptr.dtype.itemsize * 8,
+                                               N.host_ptr(idx) if n_pairs else None,
+                                               N.host_ptr(w) if n_pairs else None, N.RG_HOST))
+        return indptr, idx, w
+
+    def close(self):
+        if getattr(self, "_h", None):
+            N.lib().rg_geometry_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------------------------------
+# 2-D product requests: host-side decisions, mirrored from the reference
+# ------------------------------------------------------------------------------------------------------
+def resolve_z_limits(nz, grid_limits, z_min_idx=None, z_max_idx=None, z_min_alt=None, z_max_alt=None,
+                     have_geometry=True):
+    """Index limits of column_max/min/mean — reference products.py:462-487."""
+    if z_min_alt is not None or z_max_alt is not None:
+        if not have_geometry:
+            raise ValueError("geometry is required when using altitude-based limits")
+        z_coords = np.linspace(grid_limits[0][0], grid_limits[0][1], nz)
+        if z_min_alt is not None:
+            z_min_idx = np.searchsorted(z_coords, z_min_alt)
+        if z_max_alt is not None:
+            z_max_idx = np.searchsorted(z_coords, z_max_alt, side="right") - 1
+    if z_min_idx is None:
+        z_min_idx = 0
+    if z_max_idx is None:
+        z_max_idx = nz - 1
+    return max(0, int(z_min_idx)), min(nz - 1, int(z_max_idx))
+
+
+@dataclass
+class ColumnMax:
+    z_min_idx: Optional[int] = None
+    z_max_idx: Optional[int] = None
+    z_min_alt: Optional[float] = None
+    z_max_alt: Optional[float] = None
+    kind = N.RG_PROD_COLMAX
+    name = "column_max"
+
+    def resolve(self, grid_shape, grid_limits, have_geometry=True):
+        lo, hi = resolve_z_limits(grid_shape[0], grid_limits, self.z_min_idx, self.z_max_idx, self.z_min_alt,
+                                  self.z_max_alt, have_geometry)
+        if hi < lo:
+            raise ValueError("zero-size array to reduction operation has no identity (empty z range)")
+        return N.Product(kind=self.kind, z_lo=lo, z_hi=hi), np.float32
+
+
+class ColumnMin(ColumnMax):
+    kind = N.RG_PROD_COLMIN
+    name = "column_min"
+
+
+class ColumnMean(ColumnMax):
+    kind = N.RG_PROD_COLMEAN
+    name = "column_mean"
+
+
+@dataclass
+class CAPPI:
+    """constant_altitude_ppi — reference products.py:317-415."""
+    altitude: float
+    interpolation: str = "linear"
+    name = "cappi"
+
+    def resolve(self, grid_shape, grid_limits, have_geometry=True):
+        nz = grid_shape[0]
+        z_min, z_max = grid_limits[0]
+        altitude = self.altitude
+        if self.interpolation not in ("linear", "nearest"):
+            raise ValueError(f"Unknown interpolation method: {self.interpolation}")
+        z_coords = np.linspace(z_min, z_max, nz, dtype="float32")
+        if altitude < z_min or altitude > z_max:                      # :370-372
+            logger.warning(f"Altitude {altitude}m is outside grid range [{z_min}, {z_max}]m")
+            return None, np.float32                                   # all-NaN plane, no kernel needed
+        if self.interpolation == "nearest":                           # :377-378
+            return N.Product(kind=N.RG_PROD_LEVEL, mode=N.RG_BLEND_PICK,
+                             z_lo=int(np.argmin(np.abs(z_coords - altitude)))), np.float32
+        hit = np.isclose(z_coords, altitude, rtol=1e-6)               # :382-386
+        if np.any(hit):
+            return N.Product(kind=N.RG_PROD_LEVEL, mode=N.RG_BLEND_PICK, z_lo=int(np.where(hit)[0][0])), np.float32
+        z_step = (z_max - z_min) / (nz - 1) if nz > 1 else 1.0        # :389
+        z_frac = (altitude - z_min) / z_step
+        z_low = int(np.floor(z_frac))
+        z_high = z_low + 1
+        if z_low < 0:                                                 # :397-400
+            return N.Product(kind=N.RG_PROD_LEVEL, mode=N.RG_BLEND_PICK, z_lo=0), np.float32
+        if z_high >= nz:
+            return N.Product(kind=N.RG_PROD_LEVEL, mode=N.RG_BLEND_PICK, z_lo=nz - 1), np.float32
+        weight_high = z_frac - z_low
+        weight_low = 1.0 - weight_high
+        # NumPy (NEP 50): a Python-float weight times a float32 grid stays float32, a np.float64 weight (limits
+        # that came out of load_geometry) promotes the blend to float64 before the final float32 cast (:411-412)
+        strong = isinstance(weight_high, np.floating)
+        return N.Product(kind=N.RG_PROD_LEVEL, mode=N.RG_BLEND_F64 if strong else N.RG_BLEND_F32, z_lo=z_low,
+                         z_hi=z_high, w_lo=float(weight_low), w_hi=float(weight_high)), np.float32
+
+
+@dataclass
+class PPI:
+    """constant_elevation_ppi — reference products.py:168-314."""
+    elevation_angle: float
+    interpolation: str = "linear"
+    earth_curvature: bool = True
+    ke: float = EFFECTIVE_RADIUS_FACTOR
+    name = "ppi"
+
+    def resolve(self, grid_shape, grid_limits, have_geometry=True):
+        if self.interpolation not in ("linear", "nearest"):
+            raise ValueError(f"Unknown interpolation method: {self.interpolation}")
+        elevation_rad = np.radians(self.elevation_angle)              # products.py:70
+        ke_re = self.ke * EARTH_RADIUS
+        pr = N.Product(kind=N.RG_PROD_BEAM, mode=0 if self.interpolation == "linear" else 1,
+                       earth_curvature=1 if self.earth_curvature else 0,
+                       sin_elev=float(np.sin(elevation_rad)),
+                       cos_elev_clamped=float(np.maximum(np.cos(elevation_rad), 0.01)),
+                       tan_elev=float(np.tan(elevation_rad)), ke_re=float(ke_re), ke_re_sq=float(ke_re ** 2))
+        return pr, (np.float64 if self.interpolation == "linear" else np.float32)
+
+
+# ------------------------------------------------------------------------------------------------------
+# fused gate-mask rules
+# ------------------------------------------------------------------------------------------------------
+@dataclass
+class RangeRule:
+    """Exclude gates of `fields` where values < lo or values > hi (either bound optional)."""
+    values: object                       # float32 array of n_gates (host or device)
+    lo: Optional[float] = None
+    hi: Optional[float] = None
+    fields: Optional[Sequence[int]] = None   # indices into the gridded field list; None = all
+
+
+def _as_f32_host(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a).ravel(), dtype=np.float32)
+
+
+def _alloc_like(device: bool, shape, dtype, ref=None):
+    if not device:
+        return np.empty(shape, dtype=dtype)
+    import torch
+    tdt = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64}[np.dtype(dtype)]
+    return torch.empty(shape, dtype=tdt, device=ref.device)
+
+
+def _ptr(x, device: bool) -> int:
+    return N.device_ptr(x) if device else N.host_ptr(x)
+
+
+def _fill_nan(x, device):
+    if device:
+        x.fill_(float("nan"))
+    else:
+        x.fill(np.nan)
+
+
+def run_products(grids: Sequence, grid_shape, grid_limits, products: Sequence, z_range=None,
+                 ctx: Optional[N.Context] = None, have_geometry=True) -> List:
+    """Stand-alone K6 on existing 3-D grids (NumPy or torch CUDA float32, shape slab x ny x nx)."""
+    ctx = ctx or N.default_context()
+    device = N.is_device_array(grids[0])
+    F = len(grids)
+    nz, ny, nx = grid_shape
+    spec = _grid_spec(grid_shape, grid_limits, z_range)
+    if device:
+        held = [g.contiguous() for g in grids]
+    else:
+        held = [np.ascontiguousarray(np.asarray(g), dtype=np.float32) for g in grids]
+    n_rows = (spec.z_end - spec.z_begin) * ny * nx
+    for g in held:
+        if int(np.prod(g.shape)) != n_rows:
+            raise ValueError(f"grid has {int(np.prod(g.shape))} voxels, expected {n_rows}")
+    outs, structs = [], []
+    for p in products:
+        pr, dt = p.resolve(grid_shape, grid_limits, have_geometry)
+        out = _alloc_like(device, (F, ny, nx), dt, held[0])
+        if pr is None:
+            _fill_nan(out, device)
+        else:
+            pr.out = _ptr(out, device)
+            structs.append(pr)
+        outs.append(out)
+    if structs:
+        gp = (C.c_void_p * F)(*[_ptr(g, device) for g in held])
+        arr = (N.Product * len(structs))(*structs)
+        N.check(N.lib().rg_products(ctx.handle, C.byref(spec), F, gp, len(structs), arr,
+                                    N.RG_DEVICE if device else N.RG_HOST))
+    return outs
+
+
+def grid_fields(geom: DeviceGeometry, fields: Sequence, masks: Optional[Sequence] = None,
+                mask_invalid: Sequence[bool] | bool = False, rules: Sequence[RangeRule] = (),
+                fill_value: float = np.nan, want_grid: Sequence[bool] | bool = True, products: Sequence = (),
+                reference_order: bool = False, ctx: Optional[N.Context] = None,
+                out_grids: Optional[Sequence] = None, out_products: Optional[Sequence] = None) -> Dict[str, object]:
+    """
+    One fused pass over the neighbour table for ``len(fields)`` (<= 8) fields.
+
+    fields        list of float32 arrays of n_gates (NumPy -> the library copies H2D/D2H itself; torch CUDA
+                  tensors -> zero-copy, asynchronous on the context's stream)
+    masks         per-field boolean/uint8 arrays (True = excluded) or None
+    mask_invalid  per-field flag: treat NaN/Inf as masked (np.ma.masked_invalid semantics)
+    rules         RangeRule list, evaluated on the device and OR-ed into the masks (GateFilter fusion)
+    want_grid     per-field flag: materialise the 3-D grid
+    products      ColumnMax / ColumnMin / ColumnMean / CAPPI / PPI requests, fused in the epilogue
+    out_grids / out_products  optional preallocated outputs (e.g. pinned host arrays) of the right shape/dtype
+
+    Returns {"grids": [array or None per field], "products": [array (F, ny, nx) per request]}.
+    """
+    ctx = ctx or geom.ctx
+    F = len(fields)
+    if F < 1 or F > N.RG_MAX_FIELDS:
+        raise ValueError(f"between 1 and {N.RG_MAX_FIELDS} fields per pass")
+    device = N.is_device_array(fields[0])
+    G = geom.n_gates
+    if device:
+        fheld = [f.contiguous() for f in fields]
+        for f in fheld:
+            if f.numel() != G:
+                raise ValueError(f"field has {f.numel()} gates, geometry expects {G}")
+    else:
+        fheld = [_as_f32_host(f) for f in fields]
+        for f in fheld:
+            if f.shape[0] != G:
+                raise ValueError(f"field has {f.shape[0]} gates, geometry expects {G}")
+    mheld = [None] * F
+    if masks is not None:
+        for i, m in enumerate(masks):
+            if m is None:
+                continue
+            if device:
+                import torch
+                mheld[i] = m.contiguous().view(torch.uint8) if m.dtype == torch.bool else m.contiguous()
+            else:
+                mheld[i] = np.ascontiguousarray(np.asarray(m).ravel()).astype(np.uint8, copy=False) \
+                    if np.asarray(m).dtype != np.bool_ else np.ascontiguousarray(np.asarray(m).ravel()).view(np.uint8)
+                if mheld[i].shape[0] != G:
+                    raise ValueError("mask length does not match the number of gates")
+    if isinstance(mask_invalid, (bool, np.bool_)):
+        mask_invalid = [bool(mask_invalid)] * F
+    inv_bits = sum(1 << i for i, b in enumerate(mask_invalid) if b)
+    if isinstance(want_grid, (bool, np.bool_)):
+        want_grid = [bool(want_grid)] * F
+
+    nzs, ny, nx = geom.slab_shape
+    grids = []
+    for i in range(F):
+        if not want_grid[i]:
+            grids.append(None)
+        elif out_grids is not None and out_grids[i] is not None:
+            g = out_grids[i]
+            if int(np.prod(g.shape)) != nzs * ny * nx:
+                raise ValueError("out_grids entry has the wrong size")
+            grids.append(g)
+        else:
+            grids.append(_alloc_like(device, (nzs, ny, nx), np.float32, fheld[0]))
+
+    rheld, rstructs = [], []
+    for r in rules:
+        if r.lo is None and r.hi is None:
+            continue
+        vals = r.values.contiguous() if device else _as_f32_host(r.values)
+        for i, f in enumerate(fheld):            # alias detection keeps a single device copy
+            if (not device) and vals is not f and vals.shape == f.shape and np.shares_memory(vals, f):
+                vals = f
+        rheld.append(vals)
+        bits = (1 << F) - 1 if r.fields is None else sum(1 << int(i) for i in r.fields)
+        rstructs.append(N.QcRule(values=_ptr(vals, device), lo=0.0 if r.lo is None else float(r.lo),
+                                 hi=0.0 if r.hi is None else float(r.hi), use_lo=int(r.lo is not None),
+                                 use_hi=int(r.hi is not None), field_bits=bits))
+    if len(rstructs) > N.RG_MAX_RULES:
+        raise ValueError(f"at most {N.RG_MAX_RULES} fused range rules per pass")
+
+    pouts, pstructs = [], []
+    for k, p in enumerate(products):
+        pr, dt = p.resolve(geom.grid_shape, geom.grid_limits, True)
+        if out_products is not None and out_products[k] is not None:
+            out = out_products[k]
+        else:
+            out = _alloc_like(device, (F, ny, nx), dt, fheld[0])
+        if pr is None:
+            _fill_nan(out, device)
+        else:
+            pr.out = _ptr(out, device)
+            pstructs.append(pr)
+        pouts.append(out)
+
+    args = N.ApplyArgs()
+    args.n_fields = F
+    args.n_rules = len(rstructs)
+    args.n_products = len(pstructs)
+    args.reference_order = int(bool(reference_order))
+    args.mask_invalid_bits = inv_bits
+    args.fill_value = float(fill_value)
+    fptr = (C.c_void_p * F)(*[_ptr(f, device) for f in fheld])
+    mptr = (C.c_void_p * F)(*[(None if m is None else _ptr(m, device)) for m in mheld])
+    gptr = (C.c_void_p * F)(*[(None if g is None else _ptr(g, device)) for g in grids])
+    args.fields = fptr
+    args.masks = mptr
+    args.grid_out = gptr
+    rarr = (N.QcRule * max(len(rstructs), 1))(*rstructs)
+    parr = (N.Product * max(len(pstructs), 1))(*pstructs)
+    args.rules = rarr
+    args.products = parr
+    N.check(N.lib().rg_apply(ctx.handle, geom._h, C.byref(args), N.RG_DEVICE if device else N.RG_HOST))
+    return {"grids": grids, "products": pouts, "_keep": (fheld, mheld, rheld)}
+
+
+def warn_all_nan(kind: str, plane: np.ndarray):
+    """NumPy's nan-reductions warn when a column has no valid level; keep that observable behaviour."""
+    if np.isnan(plane).any():
+        msg = "Mean of empty slice" if kind == "mean" else "All-NaN slice encountered"
+        warnings.warn(msg, RuntimeWarning, stacklevel=3)

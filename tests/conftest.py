@@ -48,3 +48,34 @@ def assert_same(a, b, what=""):
     assert a.shape == b.shape, f"{what}: shape {a.shape} != {b.shape}"
     assert a.dtype == b.dtype, f"{what}: dtype {a.dtype} != {b.dtype}"
     np.testing.assert_array_equal(a, b, err_msg=what)
+
+
+def _has_device():
+    try:
+        from radar_grid_b200 import _native as N
+        return N.device_count() > 0
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    """gpu-marked tests need a CUDA device (or, for kernel debugging only, the dev emulator with RG_EMU=1)."""
+    have = None
+    for item in items:
+        if "gpu" in item.keywords:
+            if have is None:
+                have = _has_device()
+            if not have:
+                item.add_marker(pytest.mark.skip(reason="no CUDA device"))
+
+
+def canonical(indptr, idx, w):
+    """Sort every CSR row by gate id so two tables compare as sets."""
+    from oracle import radar_grid_oracle as O
+    return O.canonical_rows(indptr, idx, w)
+
+
+def ulp_diff_f32(a, b):
+    a = np.ascontiguousarray(a, dtype=np.float32).view(np.int32).astype(np.int64)
+    b = np.ascontiguousarray(b, dtype=np.float32).view(np.int32).astype(np.int64)
+    return np.abs(a - b)

@@ -1,0 +1,204 @@
+"""
+GPU parity tests proper: the CUDA path (through the C ABI) against the committed reference fixtures
+(tests/golden, produced by the real reference) and against the CPU oracle on the same seeded inputs.
+
+Bars (north_star): neighbour sets bit-exact; weights <= 1 float32 ulp (float64 exp differs between libm
+and CUDA by <= 1 ulp before the float32 rounding); grids/products bit-exact in reference-order mode on the
+reference's own table; fast path within 1e-4 absolute / 1e-5 relative with identical NaN mask.
+"""
+import numpy as np
+import pytest
+
+import radar_grid_b200 as rg
+from conftest import assert_same, canonical, golden_case, ulp_diff_f32
+from oracle import radar_grid_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("tiny", "barnes2", 0), ("tiny", "cressman", 0), ("tiny", "nearest", 0),
+         ("tiny", "barnes2", 350), ("small", "barnes2", 0)]
+ATOL, RTOL = 1e-4, 1e-5
+
+
+def assert_close_same_mask(a, b, what=""):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, what
+    np.testing.assert_array_equal(np.isnan(a), np.isnan(b), err_msg=f"{what}: NaN mask differs")
+    np.testing.assert_allclose(a, b, rtol=RTOL, atol=ATOL, equal_nan=True, err_msg=what)
+
+
+def build(spec, gates, weighting, alt, **kw):
+    toa = spec.toa if alt == 0 else 4000.0
+    return rg.DeviceGeometry.build(*gates, spec.grid_shape, spec.grid_limits, radar_altitude=float(alt),
+                                   min_radius=spec.min_radius, beam_factor=spec.beam_factor, weighting=weighting,
+                                   toa=toa, **kw)
+
+
+@pytest.mark.parametrize("spec_name,weighting,alt", CASES)
+def test_neighbour_table_sets_and_weights(spec_name, weighting, alt):
+    spec, radar, gates, fields, g = golden_case(spec_name, weighting, alt)
+    dev = build(spec, gates, weighting, alt)
+    indptr, idx, w = dev.export_csr()
+    assert_same(indptr.astype(np.int32), g["indptr"], "row lengths (indptr)")
+    ci, cw = canonical(indptr, idx, w)
+    ri, rw = canonical(g["indptr"], g["gate_indices"], g["weights"])
+    assert_same(ci, ri, "neighbour sets")
+    ulps = ulp_diff_f32(cw, rw)
+    assert ulps.max(initial=0) <= 1, f"weights differ by {ulps.max()} ulp"
+    assert (ulps > 0).mean() < 1e-4 if ulps.size else True
+    info = dev.info
+    assert info["n_pairs"] == len(g["gate_indices"])
+    assert info["max_row_len"] == int(np.diff(g["indptr"]).max())
+    assert info["n_empty_rows"] == int((np.diff(g["indptr"]) == 0).sum())
+
+
+def test_build_is_deterministic_and_rows_sorted_within_cells():
+    spec, radar, gates, fields, g = golden_case("tiny")
+    a = build(spec, gates, "barnes2", 0).export_csr()
+    b = build(spec, gates, "barnes2", 0).export_csr()
+    for x, y in zip(a, b):
+        assert_same(x, y, "two builds differ")
+
+
+def test_zslab_build_is_a_row_slice():
+    spec, radar, gates, fields, g = golden_case("tiny")
+    nz, ny, nx = spec.grid_shape
+    full = build(spec, gates, "barnes2", 0).export_csr()
+    slab = build(spec, gates, "barnes2", 0, z_range=(2, 5)).export_csr()
+    lo, hi = full[0][2 * ny * nx], full[0][5 * ny * nx]
+    ci, cw = canonical(slab[0], slab[1], slab[2])
+    fi, fw = canonical(full[0][2 * ny * nx:5 * ny * nx + 1] - lo, full[1][lo:hi], full[2][lo:hi])
+    assert_same(ci, fi)
+    assert_same(cw, fw)
+
+
+@pytest.mark.parametrize("spec_name,weighting,alt", CASES)
+def test_reference_order_apply_is_bit_exact_on_reference_table(spec_name, weighting, alt):
+    spec, radar, gates, fields, g = golden_case(spec_name, weighting, alt)
+    dev = rg.DeviceGeometry.from_csr(g["indptr"], g["gate_indices"], g["weights"], spec.grid_shape,
+                                     spec.grid_limits, n_gates=len(gates[0]))
+    names = list(fields)
+    data = [np.ma.getdata(fields[n]) for n in names]
+    masks = [np.ma.getmaskarray(fields[n]) for n in names]
+    res = rg.grid_fields(dev, data, masks=masks, reference_order=True)
+    for n, grid in zip(names, res["grids"]):
+        assert_same(grid, g[f"grid_{n}"], f"grid_{n}")
+    # GateFilter mask OR-ed on the host, as the reference does
+    masks_qc = [m | g["rhohv_excluded"] for m in masks]
+    res = rg.grid_fields(dev, data, masks=masks_qc, reference_order=True)
+    for n, grid in zip(names, res["grids"]):
+        assert_same(grid, g[f"gridqc_{n}"], f"gridqc_{n}")
+    res = rg.grid_fields(dev, data[:1], masks=masks[:1], fill_value=-9999.0, reference_order=True)
+    assert_same(res["grids"][0], g["grid_fill_DBZH"])
+
+
+@pytest.mark.parametrize("spec_name,weighting,alt", CASES)
+@pytest.mark.parametrize("own_table", [False, True])
+def test_fast_apply_within_tolerance(spec_name, weighting, alt, own_table):
+    spec, radar, gates, fields, g = golden_case(spec_name, weighting, alt)
+    if own_table:
+        dev = build(spec, gates, weighting, alt)
+    else:
+        dev = rg.DeviceGeometry.from_csr(g["indptr"], g["gate_indices"], g["weights"], spec.grid_shape,
+                                         spec.grid_limits, n_gates=len(gates[0]))
+    names = list(fields)
+    data = [np.ma.getdata(fields[n]) for n in names]
+    masks = [np.ma.getmaskarray(fields[n]) for n in names]
+    res = rg.grid_fields(dev, data, masks=masks)
+    for n, grid in zip(names, res["grids"]):
+        assert grid.dtype == np.float32
+        assert_close_same_mask(grid, g[f"grid_{n}"], f"grid_{n}")
+    # every group width gives the same answer up to rounding
+    for width in (4, 8, 16, 32):
+        dev.ctx.set_option("group_width", width)
+        r1 = rg.grid_fields(dev, data[:1], masks=masks[:1])
+        assert_close_same_mask(r1["grids"][0], g["grid_DBZH"], f"group_width={width}")
+        r5 = rg.grid_fields(dev, data, masks=masks)
+        assert_close_same_mask(r5["grids"][-1], g[f"grid_{names[-1]}"], f"group_width={width} 5 fields")
+    dev.ctx.set_option("group_width", 0)
+
+
+def test_fused_qc_rule_equals_host_mask_and_masked_invalid_on_device():
+    spec, radar, gates, fields, g = golden_case("small")
+    dev = build(spec, gates, "barnes2", 0)
+    names = list(fields)
+    raw = [np.ma.getdata(fields[n]).copy() for n in names]
+    for n, r in zip(names, raw):            # put the NaNs back: the device derives the masks itself
+        r[np.ma.getmaskarray(fields[n])] = np.nan
+    rhohv = raw[names.index("RHOHV")]
+    rules = [rg.RangeRule(rhohv, lo=0.8), rg.RangeRule(rhohv, hi=1.0)]
+    res = rg.grid_fields(dev, raw, mask_invalid=True, rules=rules, products=[rg.ColumnMax()])
+    for n, grid in zip(names, res["grids"]):
+        assert_close_same_mask(grid, g[f"gridqc_{n}"], f"gridqc_{n}")
+    assert_close_same_mask(res["products"][0][0], g["colmax_qc"], "fused colmax with QC")
+
+
+@pytest.mark.parametrize("spec_name,weighting,alt", CASES)
+def test_products_bit_exact_on_reference_grid(spec_name, weighting, alt):
+    spec, radar, gates, fields, g = golden_case(spec_name, weighting, alt)
+    grid = g["grid_DBZH"]
+    geom = rg.GridGeometry(spec.grid_shape, spec.grid_limits, g["indptr"], g["gate_indices"], g["weights"], spec.toa)
+    zmax = spec.grid_limits[0][1]
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        assert_same(rg.column_max(grid), g["colmax"], "colmax")
+        assert_same(rg.column_max(grid, z_min_idx=1, z_max_idx=3), g["colmax_idx_1_3"])
+        assert_same(rg.column_max(grid, z_min_alt=1500.0, z_max_alt=0.6 * zmax, geometry=geom), g["colmax_alt"])
+        assert_same(rg.column_min(grid), g["colmin"], "colmin")
+        assert_same(rg.column_mean(grid), g["colmean"], "colmean")
+        assert_same(rg.column_max(g["grid_fill_DBZH"]), g["colmax_fill"], "colmax with numeric fill")
+    for alt_m in (4000.0, 0.0, zmax, 1234.5, zmax / (spec.grid_shape[0] - 1) * 2):
+        tag = f"{alt_m:.1f}"
+        assert_same(rg.constant_altitude_ppi(grid, geom, alt_m), g[f"cappi_lin_{tag}"], f"cappi_lin {tag}")
+        assert_same(rg.constant_altitude_ppi(grid, geom, alt_m, "nearest"), g[f"cappi_near_{tag}"], f"cappi_near {tag}")
+    assert_same(rg.constant_altitude_ppi(grid, geom, zmax + 1.0), g["cappi_oob"])
+    geom64 = rg.GridGeometry(spec.grid_shape, tuple(tuple(np.float64(v) for v in l) for l in spec.grid_limits),
+                             g["indptr"], g["gate_indices"], g["weights"], spec.toa)
+    assert_same(rg.constant_altitude_ppi(grid, geom64, 1234.5), g["cappi_lin64_1234.5"], "float64-weight CAPPI")
+    for elev in (0.5, 2.3, 6.9, 25.0):
+        tag = f"{elev:.1f}"
+        assert_same(rg.constant_elevation_ppi(grid, geom, elev), g[f"ppi_lin_{tag}"], f"ppi_lin {tag}")
+        assert_same(rg.constant_elevation_ppi(grid, geom, elev, interpolation="nearest"), g[f"ppi_near_{tag}"], f"ppi_near {tag}")
+        assert_same(rg.constant_elevation_ppi(grid, geom, elev, earth_curvature=False), g[f"ppi_flat_{tag}"], f"ppi_flat {tag}")
+
+
+@pytest.mark.parametrize("reference_order", [False, True])
+def test_fused_epilogue_equals_products_of_the_grid(reference_order):
+    """COLMAX / CAPPI / PPI from the epilogue are bit-identical to the stand-alone products of the same grid,
+    and a products-only call (no 3-D output) gives the same planes."""
+    spec, radar, gates, fields, g = golden_case("small")
+    dev = build(spec, gates, "barnes2", 0)
+    names = list(fields)
+    data = [np.ma.getdata(fields[n]) for n in names]
+    masks = [np.ma.getmaskarray(fields[n]) for n in names]
+    reqs = [rg.ColumnMax(), rg.ColumnMin(z_min_idx=2, z_max_idx=7), rg.ColumnMean(), rg.CAPPI(4000.0),
+            rg.CAPPI(1234.5), rg.PPI(0.5), rg.PPI(2.3, "nearest")]
+    both = rg.grid_fields(dev, data, masks=masks, products=reqs, reference_order=reference_order)
+    only = rg.grid_fields(dev, data, masks=masks, products=reqs, want_grid=False, reference_order=reference_order)
+    assert all(x is None for x in only["grids"])
+    alone = rg.run_products(both["grids"], spec.grid_shape, spec.grid_limits, reqs)
+    for r, a, b, c in zip(reqs, both["products"], only["products"], alone):
+        assert_same(a, c, f"fused vs stand-alone: {r}")
+        assert_same(a, b, f"with vs without 3-D output: {r}")
+    # and against the oracle's products of the oracle's grid (tolerance: the grid itself is within tolerance)
+    og = O.apply_geometry(g["indptr"], g["gate_indices"], g["weights"], spec.grid_shape, fields["DBZH"])
+    assert_close_same_mask(both["products"][0][0], O.column_reduce("max", og), "colmax vs oracle")
+    assert_close_same_mask(both["products"][3][0], O.cappi(og, spec.grid_shape, spec.grid_limits, 4000.0), "cappi vs oracle")
+    assert_close_same_mask(both["products"][5][0], O.ppi(og, spec.grid_shape, spec.grid_limits, 0.5), "ppi vs oracle")
+
+
+def test_linearity_and_constant_field_properties():
+    """Size-independent properties: a constant field grids to the constant wherever defined; the operator is linear."""
+    spec, radar, gates, fields, g = golden_case("small")
+    dev = build(spec, gates, "barnes2", 0)
+    n = len(gates[0])
+    rng = np.random.default_rng(3)
+    a = rng.normal(size=n).astype(np.float32)
+    b = rng.normal(size=n).astype(np.float32)
+    const = np.full(n, 7.25, dtype=np.float32)
+    res = rg.grid_fields(dev, [a, b, (2 * a + 3 * b).astype(np.float32), const])["grids"]
+    defined = ~np.isnan(res[3])
+    np.testing.assert_array_equal(defined, np.diff(g["indptr"]).reshape(spec.grid_shape) > 0)
+    np.testing.assert_allclose(res[3][defined], 7.25, rtol=1e-6)
+    np.testing.assert_allclose(res[2][defined], (2 * res[0] + 3 * res[1])[defined], rtol=1e-4, atol=1e-4)
