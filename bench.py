@@ -146,6 +146,8 @@ def run_b200(args):
 
     stream = torch.cuda.Stream()
     ctx = N.Context(local_rank, stream.cuda_stream)
+    if os.environ.get("RG_GROUP_WIDTH"):
+        ctx.set_option("group_width", int(os.environ["RG_GROUP_WIDTH"]))
     gates = S.gate_coordinates(spec)
     t0 = time.perf_counter()
     dev = rg.DeviceGeometry.build(*gates, spec.grid_shape, spec.grid_limits, min_radius=spec.min_radius,
