@@ -146,6 +146,8 @@ def run_b200(args):
 
     stream = torch.cuda.Stream()
     ctx = N.Context(local_rank, stream.cuda_stream)
+    if os.environ.get("RG_SORT_ROWS"):
+        ctx.set_option("sort_rows", int(os.environ["RG_SORT_ROWS"]))
     if os.environ.get("RG_GROUP_WIDTH"):
         ctx.set_option("group_width", int(os.environ["RG_GROUP_WIDTH"]))
     gates = S.gate_coordinates(spec)

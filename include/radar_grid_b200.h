@@ -86,7 +86,8 @@ int rg_context_synchronize(rg_context* ctx);
 /* number of this library's kernels launched through the context so far (bench.py: gpu_launches) */
 int rg_context_kernel_launches(const rg_context* ctx, int64_t* count);
 /* options: "group_width" (0 = auto, 4/8/16/32 lanes per voxel column), "apply_variant" (0 = auto),
- * "timing" (1 = record CUDA events around every pack / apply launch, read with rg_context_kernel_time) */
+ * "timing" (1 = record CUDA events around every pack / apply launch, read with rg_context_kernel_time),
+ * "sort_rows" (default 1: rg_geometry_build orders every row by gate id) */
 int rg_context_set_option(rg_context* ctx, const char* key, int64_t value);
 /* Sum of the device time of the timed launches since the last reset: which = 0 (K4 pack), 1 (K5 apply).
  * Synchronises the stream. */

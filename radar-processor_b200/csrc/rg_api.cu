@@ -356,6 +356,7 @@ int rg_context_set_option(rg_context* c, const char* key, int64_t value)
     if (!ctx || !key) return fail(RG_ERR_INVALID, "NULL argument");
     if (strcmp(key, "apply_variant") == 0) ctx->apply_variant = value;
     else if (strcmp(key, "timing") == 0) ctx->timing = value;
+    else if (strcmp(key, "sort_rows") == 0) ctx->sort_rows = value;
     else if (strcmp(key, "group_width") == 0) {
         if (value != 0 && value != 4 && value != 8 && value != 16 && value != 32)
             return fail(RG_ERR_INVALID, "group_width must be 0, 4, 8, 16 or 32");
@@ -798,8 +799,9 @@ int rg_apply(rg_context* c, const rg_geometry* geom, const rg_apply_args* a, int
         pk.rule_use_lo[r] = q.use_lo; pk.rule_use_hi[r] = q.use_hi;
         pk.rule_bits[r] = q.field_bits;
     }
-    RG_TRY(ensure(ctx, ctx->records, std::max<size_t>((size_t)G * FP * 4, 16)));
+    RG_TRY(ensure(ctx, ctx->records, std::max<size_t>((size_t)G * FP * 4, 16) + 512));
     pk.records = (float*)ctx->records.ptr;
+    pk.records_b = (float*)((char*)ctx->records.ptr + records_b_offset(F, G));
     RG_TRY(launch_pack(ctx, pk));
 
     // ---- outputs
@@ -834,6 +836,7 @@ int rg_apply(rg_context* c, const rg_geometry* geom, const rg_apply_args* a, int
     ap.indptr = g->indptr;
     ap.pairs = g->pairs;
     ap.records = pk.records;
+    ap.records_b = pk.records_b;
     ap.ncol = ncol;
     ap.nx = g->grid.nx;
     ap.ny = g->grid.ny;

@@ -25,6 +25,8 @@
 
 #include <math.h>
 
+#include <type_traits>
+
 #include "rg_internal.cuh"
 
 namespace rg {
@@ -32,9 +34,11 @@ namespace rg {
 // ------------------------------------------------------------------------------------------------------
 // K4  pack: gate masks (field mask | masked_invalid | fused QC range rules) + AoS records
 // ------------------------------------------------------------------------------------------------------
-template <int FP>
+template <int FA, int FB>
 __global__ void __launch_bounds__(256) pack_records_kernel(const __grid_constant__ PackParams p)
 {
+    // FB == 0: one AoS array of FA floats per gate.  FB > 0 (RG_VAR 2): fields 0..FA-1 in array A, FA.. in array B.
+    constexpr int NV = FA + FB;
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= p.n_gates) return;
 
@@ -46,9 +50,9 @@ __global__ void __launch_bounds__(256) pack_records_kernel(const __grid_constant
         if (hit) excluded |= p.rule_bits[r];
     }
 
-    float out[FP];
+    float out[NV];
 #pragma unroll
-    for (int f = 0; f < FP; ++f) {
+    for (int f = 0; f < NV; ++f) {
         uint32_t bits = kMaskedBits;
         if (f < p.n_fields) {
             const float v = __ldg(p.fields[f] + g);
@@ -59,32 +63,50 @@ __global__ void __launch_bounds__(256) pack_records_kernel(const __grid_constant
         }
         out[f] = __uint_as_float(bits);
     }
-    float* dst = p.records + (size_t)g * FP;
-    if constexpr (FP == 1) {
-        dst[0] = out[0];
-    } else if constexpr (FP == 2) {
-        *reinterpret_cast<float2*>(dst) = make_float2(out[0], out[1]);
-    } else if constexpr (FP == 4) {
-        *reinterpret_cast<float4*>(dst) = make_float4(out[0], out[1], out[2], out[3]);
-    } else {
-        reinterpret_cast<float4*>(dst)[0] = make_float4(out[0], out[1], out[2], out[3]);
-        reinterpret_cast<float4*>(dst)[1] = make_float4(out[4], out[5], out[6], out[7]);
-    }
+    auto store = [](float* dst, const float* v, auto n) {
+        constexpr int N = decltype(n)::value;
+        if constexpr (N == 1) dst[0] = v[0];
+        else if constexpr (N == 2) *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
+        else if constexpr (N == 4) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+        else {
+            reinterpret_cast<float4*>(dst)[0] = make_float4(v[0], v[1], v[2], v[3]);
+            reinterpret_cast<float4*>(dst)[1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+    };
+    store(p.records + (size_t)g * FA, out, std::integral_constant<int, FA>{});
+    if constexpr (FB > 0) store(p.records_b + (size_t)g * FB, out + FA, std::integral_constant<int, FB>{});
 }
 
 int records_width(int n_fields) { return n_fields <= 1 ? 1 : n_fields == 2 ? 2 : n_fields <= 4 ? 4 : 8; }
+
+size_t records_b_offset(int n_fields, int64_t n_gates)
+{
+    const int fa = n_fields == 1 ? 1 : n_fields == 2 ? 2 : 4;
+    return (((size_t)n_gates * fa * sizeof(float)) + 255) & ~(size_t)255;
+}
 
 int launch_pack(Context* ctx, const PackParams& p)
 {
     if (p.n_gates == 0) return RG_OK;
     const unsigned blocks = (unsigned)((p.n_gates + 255) / 256);
     timer_begin(ctx, kTimerPack);
-    switch (records_width(p.n_fields)) {
-        case 1: pack_records_kernel<1><<<blocks, 256, 0, ctx->stream>>>(p); break;
-        case 2: pack_records_kernel<2><<<blocks, 256, 0, ctx->stream>>>(p); break;
-        case 4: pack_records_kernel<4><<<blocks, 256, 0, ctx->stream>>>(p); break;
-        default: pack_records_kernel<8><<<blocks, 256, 0, ctx->stream>>>(p); break;
+#if RG_VAR == 2
+    switch (p.n_fields) {
+        case 1: pack_records_kernel<1, 0><<<blocks, 256, 0, ctx->stream>>>(p); break;
+        case 2: pack_records_kernel<2, 0><<<blocks, 256, 0, ctx->stream>>>(p); break;
+        case 3: case 4: pack_records_kernel<4, 0><<<blocks, 256, 0, ctx->stream>>>(p); break;
+        case 5: pack_records_kernel<4, 1><<<blocks, 256, 0, ctx->stream>>>(p); break;
+        case 6: pack_records_kernel<4, 2><<<blocks, 256, 0, ctx->stream>>>(p); break;
+        default: pack_records_kernel<4, 4><<<blocks, 256, 0, ctx->stream>>>(p); break;
     }
+#else
+    switch (records_width(p.n_fields)) {
+        case 1: pack_records_kernel<1, 0><<<blocks, 256, 0, ctx->stream>>>(p); break;
+        case 2: pack_records_kernel<2, 0><<<blocks, 256, 0, ctx->stream>>>(p); break;
+        case 4: pack_records_kernel<4, 0><<<blocks, 256, 0, ctx->stream>>>(p); break;
+        default: pack_records_kernel<8, 0><<<blocks, 256, 0, ctx->stream>>>(p); break;
+    }
+#endif
     timer_end(ctx, kTimerPack);
     ctx->launches++;
     RG_CUDA(cudaGetLastError());
@@ -264,20 +286,40 @@ int launch_products(Context* ctx, const rg_grid_spec& grid, int n_fields, const 
 
 // ------------------------------------------------------------------------------------------------------
 // K5  fast path: column-tile CSR gather, W lanes per column, products in the epilogue
+//
+// Gate-record layouts (RG_VAR, a build-time choice so that variants can be measured side by side):
+//   0  AoS  float[G][FP]            masked values zeroed with selects           (first version, kept for A/B)
+//   1  AoS  float[G][FP]            predicated accumulate
+//   2  split A = float[G][FA] (fields 0..3) + B = float[G][FB] (fields 4..7), predicated accumulate:
+//      20 B per gate instead of 32 for five fields, no padding work
+//   3  AoS 32 B, two lanes per record: lane h of a pair loads half h (16 B) of two consecutive pairs'
+//      records, so one load instruction touches each 128-byte line once instead of twice
 // ------------------------------------------------------------------------------------------------------
-template <int FP>
-__device__ __forceinline__ void load_record(const float* __restrict__ rec, uint32_t gate, float (&v)[FP])
+template <int F>
+struct Layout {
+    static constexpr int FP = F == 1 ? 1 : F == 2 ? 2 : F <= 4 ? 4 : 8;
+    static constexpr int FA = F == 1 ? 1 : F == 2 ? 2 : 4;
+    static constexpr int FB = F <= 4 ? 0 : F == 5 ? 1 : F == 6 ? 2 : 4;
+#if RG_VAR == 2
+    static constexpr int NV = FA + FB;
+#else
+    static constexpr int NV = FP;
+#endif
+};
+
+template <int N>
+__device__ __forceinline__ void load_vec(const float* __restrict__ base, uint32_t gate, float* v)
 {
-    if constexpr (FP == 1) {
-        v[0] = __ldg(rec + gate);
-    } else if constexpr (FP == 2) {
-        const float2 t = __ldg(reinterpret_cast<const float2*>(rec) + gate);
+    if constexpr (N == 1) {
+        v[0] = __ldg(base + gate);
+    } else if constexpr (N == 2) {
+        const float2 t = __ldg(reinterpret_cast<const float2*>(base) + gate);
         v[0] = t.x; v[1] = t.y;
-    } else if constexpr (FP == 4) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(rec) + gate);
+    } else if constexpr (N == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(base) + gate);
         v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-    } else {
-        const float4* q = reinterpret_cast<const float4*>(rec) + 2 * (size_t)gate;
+    } else if constexpr (N == 8) {
+        const float4* q = reinterpret_cast<const float4*>(base) + 2 * (size_t)gate;
         const float4 a = __ldg(q);
         const float4 b = __ldg(q + 1);
         v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
@@ -285,45 +327,66 @@ __device__ __forceinline__ void load_record(const float* __restrict__ rec, uint3
     }
 }
 
-template <int F, int FP>
-__device__ __forceinline__ void accumulate(float w, const float (&v)[FP], float (&swv)[F], float (&sw)[F])
+template <int F>
+__device__ __forceinline__ void load_record(const float* __restrict__ rec, const float* __restrict__ rec_b, uint32_t gate,
+                                            float (&v)[Layout<F>::NV])
+{
+#if RG_VAR == 2
+    load_vec<Layout<F>::FA>(rec, gate, v);
+    if constexpr (Layout<F>::FB > 0) load_vec<Layout<F>::FB>(rec_b, gate, v + Layout<F>::FA);
+#else
+    load_vec<Layout<F>::FP>(rec, gate, v);
+#endif
+}
+
+template <int F, int NV>
+__device__ __forceinline__ void accumulate(float w, const float (&v)[NV], float (&swv)[F], float (&sw)[F])
 {
 #pragma unroll
     for (int f = 0; f < F; ++f) {
         const bool m = __float_as_uint(v[f]) == kMaskedBits;   // interpolate.py:78-79
+#if RG_VAR == 0
         const float we = m ? 0.f : w;
         const float vv = m ? 0.f : v[f];
         sw[f] = __fadd_rn(sw[f], we);
         swv[f] = fmaf(we, vv, swv[f]);
+#else
+        if (!m) {
+            sw[f] = __fadd_rn(sw[f], w);
+            swv[f] = fmaf(w, v[f], swv[f]);
+        }
+#endif
     }
 }
 
 // Sum pairs [p, e) with stride `step`, four pairs (and their gathers) in flight per lane.
-template <int F, int FP>
+template <int F>
 __device__ __forceinline__ void gather_run(const uint2* __restrict__ pairs, const float* __restrict__ rec,
-                                           uint32_t p, uint32_t e, uint32_t step, float (&swv)[F], float (&sw)[F])
+                                           const float* __restrict__ rec_b, uint32_t p, uint32_t e, uint32_t step,
+                                           float (&swv)[F], float (&sw)[F])
 {
+    constexpr int NV = Layout<F>::NV;
     while (p < e && e - p > 3 * step) {
         const uint2 a0 = __ldcs(pairs + p);
         const uint2 a1 = __ldcs(pairs + p + step);
         const uint2 a2 = __ldcs(pairs + p + 2 * step);
         const uint2 a3 = __ldcs(pairs + p + 3 * step);
-        float v0[FP], v1[FP], v2[FP], v3[FP];
-        load_record<FP>(rec, a0.x, v0);
-        load_record<FP>(rec, a1.x, v1);
-        load_record<FP>(rec, a2.x, v2);
-        load_record<FP>(rec, a3.x, v3);
-        accumulate<F, FP>(__uint_as_float(a0.y), v0, swv, sw);
-        accumulate<F, FP>(__uint_as_float(a1.y), v1, swv, sw);
-        accumulate<F, FP>(__uint_as_float(a2.y), v2, swv, sw);
-        accumulate<F, FP>(__uint_as_float(a3.y), v3, swv, sw);
+        float v0[NV], v1[NV], v2[NV], v3[NV];
+        load_record<F>(rec, rec_b, a0.x, v0);
+        load_record<F>(rec, rec_b, a1.x, v1);
+        load_record<F>(rec, rec_b, a2.x, v2);
+        load_record<F>(rec, rec_b, a3.x, v3);
+        accumulate<F, NV>(__uint_as_float(a0.y), v0, swv, sw);
+        accumulate<F, NV>(__uint_as_float(a1.y), v1, swv, sw);
+        accumulate<F, NV>(__uint_as_float(a2.y), v2, swv, sw);
+        accumulate<F, NV>(__uint_as_float(a3.y), v3, swv, sw);
         p += 4 * step;
     }
     while (p < e) {
         const uint2 a0 = __ldcs(pairs + p);
-        float v0[FP];
-        load_record<FP>(rec, a0.x, v0);
-        accumulate<F, FP>(__uint_as_float(a0.y), v0, swv, sw);
+        float v0[NV];
+        load_record<F>(rec, rec_b, a0.x, v0);
+        accumulate<F, NV>(__uint_as_float(a0.y), v0, swv, sw);
         p += step;
     }
 }
@@ -331,7 +394,6 @@ __device__ __forceinline__ void gather_run(const uint2* __restrict__ pairs, cons
 template <int F, int W, bool PROD>
 __global__ void __launch_bounds__(kApplyThreads) apply_columns_kernel(const __grid_constant__ ApplyParams p)
 {
-    constexpr int FP = F == 1 ? 1 : F == 2 ? 2 : F <= 4 ? 4 : 8;
     static_assert(W >= F || W == 32, "one lane per field in the epilogue");
     constexpr unsigned kFull = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
@@ -343,6 +405,7 @@ __global__ void __launch_bounds__(kApplyThreads) apply_columns_kernel(const __gr
     const uint32_t* __restrict__ indptr = p.indptr;
     const uint2* __restrict__ pairs = p.pairs;
     const float* __restrict__ rec = p.records;
+    const float* __restrict__ rec_b = p.records_b;
 
     float x = 0.f, y = 0.f;
     ColumnState st;
@@ -387,7 +450,7 @@ __global__ void __launch_bounds__(kApplyThreads) apply_columns_kernel(const __gr
                 float hwv[F], hw[F];
 #pragma unroll
                 for (int f = 0; f < F; ++f) { hwv[f] = 0.f; hw[f] = 0.f; }
-                gather_run<F, FP>(pairs, rec, hs + lane, he, 32, hwv, hw);
+                gather_run<F>(pairs, rec, rec_b, hs + lane, he, 32, hwv, hw);
 #pragma unroll
                 for (int f = 0; f < F; ++f) {
 #pragma unroll
@@ -405,7 +468,7 @@ __global__ void __launch_bounds__(kApplyThreads) apply_columns_kernel(const __gr
             heavy_mine = false;
         }
 
-        if (!heavy_mine) gather_run<F, FP>(pairs, rec, s + gl, e, W, swv, sw);
+        if (!heavy_mine) gather_run<F>(pairs, rec, rec_b, s + gl, e, W, swv, sw);
 
         // butterfly inside the group: afterwards every lane of the group holds the row sums
 #pragma unroll
@@ -435,6 +498,158 @@ __global__ void __launch_bounds__(kApplyThreads) apply_columns_kernel(const __gr
     }
 }
 
+#if RG_VAR == 3
+// Lane-paired variant (32-byte records, F >= 5, 8 lanes per column = 4 slots x 2 halves).
+// Slot q of a group handles two consecutive pairs per step; lane h of the slot loads half h (fields 4h..4h+3)
+// of both records.  The group's partial sums are then reduced AND scattered in one go: after two halving
+// exchanges lane (h, q) holds the row total of field 4h + 2(q&1) + (q>>1), which it finishes itself.
+__device__ __forceinline__ void acc_half(float w, const float4& r, float (&swv)[4], float (&sw)[4])
+{
+    const float v[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+        if (__float_as_uint(v[f]) != kMaskedBits) {
+            sw[f] = __fadd_rn(sw[f], w);
+            swv[f] = fmaf(w, v[f], swv[f]);
+        }
+    }
+}
+
+__device__ __forceinline__ void paired_run(const uint2* __restrict__ pairs, const float* __restrict__ rec, uint32_t s,
+                                           uint32_t e, uint32_t slot, uint32_t nslots, int h, float (&swv)[4], float (&sw)[4])
+{
+    const float4* __restrict__ rec4 = reinterpret_cast<const float4*>(rec);
+    const float mb = __uint_as_float(kMaskedBits);
+    const float4 masked = make_float4(mb, mb, mb, mb);
+    const uint32_t stride = 2 * nslots;
+    uint32_t p0 = s + 2 * slot;
+    while (p0 < e && e - p0 > stride + 1) {                    // two full steps: pairs p0, p0+1, p0+stride, p0+stride+1
+        const uint2 a0 = __ldcs(pairs + p0);
+        const uint2 a1 = __ldcs(pairs + p0 + 1);
+        const uint2 a2 = __ldcs(pairs + p0 + stride);
+        const uint2 a3 = __ldcs(pairs + p0 + stride + 1);
+        const float4 r0 = __ldg(rec4 + 2 * (size_t)a0.x + h);
+        const float4 r1 = __ldg(rec4 + 2 * (size_t)a1.x + h);
+        const float4 r2 = __ldg(rec4 + 2 * (size_t)a2.x + h);
+        const float4 r3 = __ldg(rec4 + 2 * (size_t)a3.x + h);
+        acc_half(__uint_as_float(a0.y), r0, swv, sw);
+        acc_half(__uint_as_float(a1.y), r1, swv, sw);
+        acc_half(__uint_as_float(a2.y), r2, swv, sw);
+        acc_half(__uint_as_float(a3.y), r3, swv, sw);
+        p0 += 2 * stride;
+    }
+    while (p0 < e) {
+        const bool two = p0 + 1 < e;
+        const uint2 a0 = __ldcs(pairs + p0);
+        const uint2 a1 = two ? __ldcs(pairs + p0 + 1) : make_uint2(0u, 0u);
+        const float4 r0 = __ldg(rec4 + 2 * (size_t)a0.x + h);
+        const float4 r1 = two ? __ldg(rec4 + 2 * (size_t)a1.x + h) : masked;
+        acc_half(__uint_as_float(a0.y), r0, swv, sw);
+        acc_half(__uint_as_float(a1.y), r1, swv, sw);
+        p0 += stride;
+    }
+}
+
+template <int F, bool PROD>
+__global__ void __launch_bounds__(kApplyThreads) apply_columns_paired_kernel(const __grid_constant__ ApplyParams p)
+{
+    static_assert(F >= 5 && F <= 8, "paired layout is for 32-byte records");
+    constexpr unsigned kFull = 0xFFFFFFFFu;
+    constexpr int W = 8;
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & 7;
+    const int h = gl & 1;                                      // record half
+    const int q = gl >> 1;                                     // slot in the group
+    const int fld = 4 * h + 2 * (q & 1) + (q >> 1);            // field this lane finishes
+    const int64_t col = (int64_t)blockIdx.x * (kApplyThreads / W) + threadIdx.x / W;
+    const bool col_ok = col < p.ncol;
+    const bool owner = col_ok && fld < F;
+
+    const uint32_t* __restrict__ indptr = p.indptr;
+    const uint2* __restrict__ pairs = p.pairs;
+    const float* __restrict__ rec = p.records;
+
+    float x = 0.f, y = 0.f;
+    ColumnState st;
+    if constexpr (PROD) {
+        if (owner) {
+            x = __ldg(p.prod.x_ax + (int)(col % p.nx));
+            y = __ldg(p.prod.y_ax + (int)(col / p.nx));
+        }
+        st.init(p.prod, x, y);
+    }
+
+    uint32_t s_next = 0, e_next = 0;
+    if (col_ok && p.lz_first < p.lz_last) {
+        const size_t row = (size_t)p.lz_first * (size_t)p.ncol + (size_t)col;
+        s_next = __ldg(indptr + row);
+        e_next = __ldg(indptr + row + 1);
+    }
+
+    for (int lz = p.lz_first; lz < p.lz_last; ++lz) {
+        const uint32_t s = s_next, e = e_next;
+        const size_t row = (size_t)lz * (size_t)p.ncol + (size_t)col;
+        if (col_ok && lz + 1 < p.lz_last) {
+            s_next = __ldg(indptr + row + (size_t)p.ncol);
+            e_next = __ldg(indptr + row + (size_t)p.ncol + 1);
+        }
+        float swv[4] = {0.f, 0.f, 0.f, 0.f}, sw[4] = {0.f, 0.f, 0.f, 0.f};
+        const uint32_t len = e - s;
+        const bool heavy_mine = len > kHeavyRow;
+        unsigned heavy = __ballot_sync(kFull, heavy_mine && gl == 0);
+        while (heavy) {
+            const int src = __ffs(heavy) - 1;
+            heavy &= heavy - 1;
+            const uint32_t hs = __shfl_sync(kFull, s, src);
+            const uint32_t he = __shfl_sync(kFull, e, src);
+            float hwv[4] = {0.f, 0.f, 0.f, 0.f}, hw[4] = {0.f, 0.f, 0.f, 0.f};
+            paired_run(pairs, rec, hs, he, (uint32_t)(lane >> 1), 16u, h, hwv, hw);
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+#pragma unroll
+                for (int off = 16; off >= 2; off >>= 1) {      // over the 16 slots, halves stay apart
+                    hwv[f] += __shfl_xor_sync(kFull, hwv[f], off);
+                    hw[f] += __shfl_xor_sync(kFull, hw[f], off);
+                }
+            }
+            if ((lane & ~1) == src) {                          // slot 0 of the owning group keeps the total
+#pragma unroll
+                for (int f = 0; f < 4; ++f) { swv[f] = hwv[f]; sw[f] = hw[f]; }
+            }
+        }
+        if (!heavy_mine) paired_run(pairs, rec, s, e, (uint32_t)q, 4u, h, swv, sw);
+
+        // reduce-scatter over the 4 slots: 6 shuffles instead of 16
+        float n_wv[2], n_w[2];
+        {
+            const bool up = q & 1;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const float send_wv = up ? swv[j] : swv[j + 2];
+                const float send_w = up ? sw[j] : sw[j + 2];
+                const float keep_wv = up ? swv[j + 2] : swv[j];
+                const float keep_w = up ? sw[j + 2] : sw[j];
+                n_wv[j] = keep_wv + __shfl_xor_sync(kFull, send_wv, 2);
+                n_w[j] = keep_w + __shfl_xor_sync(kFull, send_w, 2);
+            }
+        }
+        const bool up2 = q >> 1;
+        const float a = (up2 ? n_wv[1] : n_wv[0]) + __shfl_xor_sync(kFull, up2 ? n_wv[0] : n_wv[1], 4);
+        const float b = (up2 ? n_w[1] : n_w[0]) + __shfl_xor_sync(kFull, up2 ? n_w[0] : n_w[1], 4);
+
+        if (owner) {
+            const float v = b > 0.f ? __fdiv_rn(a, b) : p.fill;
+            float* out = p.grid_out[fld];
+            if (out != nullptr) __stcs(out + row, v);
+            if constexpr (PROD) st.update(p.prod, p.z_begin + lz, v);
+        }
+    }
+    if constexpr (PROD) {
+        if (owner) st.write(p.prod, fld, col, p.ncol, x, y);
+    }
+}
+#endif  // RG_VAR == 3
+
 // ------------------------------------------------------------------------------------------------------
 // K5  reference-order path: reproduces np.add.reduceat's summation order, so that on the reference's own
 //     table (KD-tree row order) the grid is bit-identical to interpolate.py's.  One thread per row.
@@ -447,10 +662,12 @@ struct RowTerms {
     const float* rec;
     int field;
     bool weights_only;
+    int stride;        // floats per gate in the array `rec` points at
+    int offset;        // position of the field inside its record
     __device__ __forceinline__ float at(uint32_t i) const
     {
         const uint2 pr = __ldg(pairs + i);
-        const float v = __ldg(rec + (size_t)pr.x * FP + field);
+        const float v = __ldg(rec + (size_t)pr.x * stride + offset);
         const bool m = __float_as_uint(v) == kMaskedBits;
         const float we = m ? 0.f : __uint_as_float(pr.y);
         if (weights_only) return we;
@@ -527,7 +744,13 @@ __global__ void __launch_bounds__(128) apply_reference_order_kernel(const __grid
         if (out == nullptr) continue;
         float v = p.fill;
         if (e > s) {
-            RowTerms<FP> t{p.pairs, p.records, f, false};
+#if RG_VAR == 2
+            const int fa = p.n_fields == 1 ? 1 : p.n_fields == 2 ? 2 : 4;
+            const int fb = p.n_fields <= 4 ? 0 : p.n_fields == 5 ? 1 : p.n_fields == 6 ? 2 : 4;
+            RowTerms<FP> t{p.pairs, f < fa ? p.records : p.records_b, f, false, f < fa ? fa : fb, f < fa ? f : f - fa};
+#else
+            RowTerms<FP> t{p.pairs, p.records, f, false, FP, f};
+#endif
             float swv = t.at(s);
             if (e - s > 1) swv = __fadd_rn(swv, pairwise_sum<FP>(t, s + 1, e - s - 1));
             t.weights_only = true;
@@ -554,6 +777,14 @@ static void launch_columns(Context* ctx, const ApplyParams& p)
 template <int F>
 static int launch_columns_w(Context* ctx, const ApplyParams& p, int W)
 {
+#if RG_VAR == 3
+    if constexpr (F >= 5) {
+        const unsigned blocks = (unsigned)((p.ncol + 31) / 32);
+        if (p.prod.any) apply_columns_paired_kernel<F, true><<<blocks, kApplyThreads, 0, ctx->stream>>>(p);
+        else apply_columns_paired_kernel<F, false><<<blocks, kApplyThreads, 0, ctx->stream>>>(p);
+        return RG_OK;
+    }
+#endif
     if constexpr (F <= 4) {
         if (W == 4) { launch_columns<F, 4>(ctx, p); return RG_OK; }
     }

@@ -8,6 +8,10 @@
 
 #include "radar_grid_b200.h"
 
+#ifndef RG_VAR
+#define RG_VAR 1          // gate-record layout / accumulate variant of the apply kernel, see rg_apply.cu
+#endif
+
 namespace rg {
 
 // ---- error plumbing ---------------------------------------------------------------------------------
@@ -74,6 +78,7 @@ struct Context {
     int64_t group_width = 0;             // 0 = auto
     int sm_count = 148;
     int64_t timing = 0;                  // record events around pack/apply launches
+    int64_t sort_rows = 1;               // geometry build: order every row by gate id
     KernelTimer timers[kTimerCount];
     Scratch records;                     // packed gate records
     Scratch stage_in;                    // H2D staging of fields / masks / rule values
@@ -116,7 +121,8 @@ struct ProductParams {
 struct ApplyParams {
     const uint32_t* indptr;
     const uint2* pairs;
-    const float* records;                 // [n_gates][FP]
+    const float* records;                 // [n_gates][FP]  (RG_VAR 2: fields 0..3)
+    const float* records_b;               // RG_VAR 2: fields 4..7
     int64_t ncol;                         // ny*nx
     int32_t nx, ny;
     int32_t z_begin;                      // global index of local level 0
@@ -139,10 +145,12 @@ struct PackParams {
     int32_t rule_use_lo[RG_MAX_RULES], rule_use_hi[RG_MAX_RULES];
     uint32_t rule_bits[RG_MAX_RULES];
     float* records;
+    float* records_b;
 };
 
 // ---- launchers (defined in the .cu files) -----------------------------------------------------------
 int records_width(int n_fields);          // floats per packed gate record: 1, 2, 4 or 8
+size_t records_b_offset(int n_fields, int64_t n_gates);   // byte offset of array B inside the record buffer (RG_VAR 2)
 int launch_pack(Context* ctx, const PackParams& p);
 int launch_apply(Context* ctx, const Geometry* g, const ApplyParams& p, bool reference_order);
 int launch_products(Context* ctx, const rg_grid_spec& grid, int n_fields, const float* const* grids_dev,

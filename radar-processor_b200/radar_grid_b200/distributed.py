@@ -1,0 +1,102 @@
+"""
+Multi-GPU sharding of the gridding path — one process per GPU, torch.distributed for the plumbing.
+
+The path shards two ways, neither of which the reference has (it only has a
+multiprocessing.Pool over z-levels inside the table build, compute.py:203-222):
+
+  volume batch   volumes of one scan strategy are independent given the neighbour table: every rank holds a
+                 replica of the table (built locally on its GPU) and grids the volume ids `shard_volumes`
+                 assigns to it.  No data-path collective; results stay on the rank or are gathered to rank 0.
+  z-slab         voxel rows are z-major, so a z-slab is a contiguous CSR row range: every rank builds and
+                 holds only its slab (`zslab_ranges`), grids it, and the partial COLMAX planes are combined by
+                 ONE all-reduce(max) over NCCL/NVLink (`allreduce_nanmax`; NaN = "no data" is carried as -inf
+                 because max(NaN, x) is unspecified in NCCL).  3-D grids need no exchange: slabs concatenate.
+
+The collective helpers work on CPU tensors with the gloo backend too, which is how the host-side logic is
+tested without GPUs.
+"""
+
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+
+def shard_volumes(n_volumes: int, world_size: int, rank: int) -> List[int]:
+    """Round-robin assignment of volume ids to ranks (balanced to within one volume)."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank outside [0, world_size)")
+    return list(range(rank, n_volumes, world_size))
+
+
+def zslab_ranges(nz: int, world_size: int) -> List[Tuple[int, int]]:
+    """Contiguous [z0, z1) level ranges, one per rank, sizes differing by at most one level."""
+    if world_size < 1 or nz < 0:
+        raise ValueError("bad arguments")
+    base, extra = divmod(nz, world_size)
+    out, z = [], 0
+    for r in range(world_size):
+        n = base + (1 if r < extra else 0)
+        out.append((z, z + n))
+        z += n
+    return out
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def allreduce_nanmax(plane, group=None, minimum: bool = False):
+    """
+    In-place combine of partial column-max (or -min) planes across ranks with NumPy's nanmax semantics:
+    a pixel is NaN only if it is NaN on every rank.  `plane` is a torch tensor (CUDA with nccl, CPU with gloo).
+    """
+    import torch
+    dist = _dist()
+    sentinel = float("inf") if minimum else float("-inf")
+    nan = torch.isnan(plane)
+    plane.masked_fill_(nan, sentinel)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(plane, op=dist.ReduceOp.MIN if minimum else dist.ReduceOp.MAX, group=group)
+    plane.masked_fill_(plane == sentinel, float("nan"))
+    return plane
+
+
+def allreduce_nanmean(total, count, group=None):
+    """Column mean across slabs: sums and valid counts are added, then divided (NaN where the count is 0)."""
+    dist = _dist()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(count, op=dist.ReduceOp.SUM, group=group)
+    return total / count
+
+
+def gather_to_rank0(local: Dict[int, np.ndarray], group=None) -> Optional[Dict[int, np.ndarray]]:
+    """Collect {volume id: result} dictionaries on rank 0 (host-side gather of small 2-D products)."""
+    dist = _dist()
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return dict(local)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    bucket = [None] * world if rank == 0 else None
+    dist.gather_object(local, bucket, dst=0, group=group)
+    if rank != 0:
+        return None
+    merged: Dict[int, np.ndarray] = {}
+    for part in bucket:
+        merged.update(part)
+    return merged
+
+
+def grid_volume_batch(volume_ids: Sequence[int], load_volume: Callable[[int], Sequence], grid_one: Callable) -> Dict[int, object]:
+    """Grid this rank's share of a time series.  `grid_one(fields)` is normally a closure over
+    ``engine.grid_fields`` and the rank's table replica; it is injectable so the sharding logic can be tested on CPU."""
+    return {vid: grid_one(load_volume(vid)) for vid in volume_ids}
+
+
+def colmax_zslab(grid_slab: Callable[[], "object"], group=None):
+    """z-slab COLMAX: `grid_slab()` returns this rank's partial COLMAX planes (torch tensor, NaN = no data),
+    e.g. from ``grid_fields(slab_geometry, ..., products=[ColumnMax()], want_grid=False)``; the result is the
+    global COLMAX on every rank."""
+    return allreduce_nanmax(grid_slab(), group=group)

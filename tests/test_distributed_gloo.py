@@ -1,0 +1,85 @@
+"""
+Host-side logic of the multi-GPU paths on CPU: world_size-2 gloo process groups.  The per-rank compute is
+the oracle here (tests may use it); on GPUs it is grid_fields on the rank's table replica / z-slab.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import golden_case, load_golden
+from radar_grid_b200 import distributed as D
+
+
+def test_shard_volumes_partition():
+    for n, w in ((256, 8), (10, 4), (3, 8), (0, 2)):
+        shards = [D.shard_volumes(n, w, r) for r in range(w)]
+        flat = sorted(v for s in shards for v in s)
+        assert flat == list(range(n))
+        assert max(len(s) for s in shards) - min(len(s) for s in shards) <= 1
+    with pytest.raises(ValueError):
+        D.shard_volumes(4, 2, 2)
+
+
+def test_zslab_ranges_cover_contiguously():
+    for nz, w in ((80, 8), (40, 3), (5, 8), (20, 1)):
+        r = D.zslab_ranges(nz, w)
+        assert r[0][0] == 0 and r[-1][1] == nz and len(r) == w
+        assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        sizes = [b - a for a, b in r]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from oracle import radar_grid_oracle as O
+        spec, radar, gates, fields, g = golden_case("tiny")
+        nz, ny, nx = spec.grid_shape
+        # --- z-slab COLMAX: partial nanmax of this rank's levels, one all-reduce(max)
+        z0, z1 = D.zslab_ranges(nz, world)[rank]
+        lo, hi = g["indptr"][z0 * ny * nx], g["indptr"][z1 * ny * nx]
+        slab = O.apply_geometry(g["indptr"][z0 * ny * nx:z1 * ny * nx + 1] - lo, g["gate_indices"][lo:hi],
+                                g["weights"][lo:hi], (z1 - z0, ny, nx), fields["DBZH"])
+        assert np.array_equal(slab, g["grid_DBZH"][z0:z1], equal_nan=True)
+        partial = torch.from_numpy(O.column_reduce("max", slab).copy())
+        full = D.colmax_zslab(lambda: partial).numpy()
+        assert np.array_equal(full, g["colmax"], equal_nan=True), "z-slab COLMAX != reference COLMAX"
+        pmin = torch.from_numpy(O.column_reduce("min", slab).copy())
+        assert np.array_equal(D.allreduce_nanmax(pmin, minimum=True).numpy(), g["colmin"], equal_nan=True)
+        # --- volume batch: each rank grids its share, rank 0 gathers
+        ids = D.shard_volumes(5, world, rank)
+        local = D.grid_volume_batch(ids, lambda vid: vid, lambda v: np.full((2, 2), float(v)))
+        merged = D.gather_to_rank0(local)
+        if rank == 0:
+            assert sorted(merged) == list(range(5)) and all(merged[v][0, 0] == v for v in merged)
+        else:
+            assert merged is None
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
+def test_allreduce_nanmax_single_process_semantics():
+    p = torch.tensor([[1.0, float("nan")], [float("nan"), -2.0]])
+    out = D.allreduce_nanmax(p.clone())
+    assert torch.equal(torch.isnan(out), torch.isnan(p)) and out[0, 0] == 1.0 and out[1, 1] == -2.0

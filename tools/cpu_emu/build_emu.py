@@ -83,7 +83,7 @@ def main():
         open(dst, "w").write(rewrite_launches(src))
         cpps.append(dst)
     lib = os.path.join(OUT, "libradargrid_b200_emu.so")
-    cmd = ["g++", "-std=c++20", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-Wno-unknown-pragmas",
+    cmd = ["g++", "-std=c++20", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-Wno-unknown-pragmas", *os.environ.get("RG_EMU_FLAGS", "").split(),
            "-I", HERE, "-I", CSRC, "-I", os.path.join(ROOT, "include"), "-o", lib] + cpps
     res = subprocess.run(cmd, capture_output=True, text=True)
     sys.stderr.write(res.stderr[-6000:])

@@ -90,6 +90,7 @@ inline unsigned __reduce_max_sync(unsigned, unsigned v)
     emu_self.warp->bar->arrive_and_wait();
     return m;
 }
+inline void __syncwarp() { emu_self.warp->bar->arrive_and_wait(); }
 inline void __syncthreads() { emu_self.block_bar->arrive_and_wait(); }
 
 // ---- scalar intrinsics -------------------------------------------------------------------------------------
