@@ -146,6 +146,8 @@ def run_b200(args):
 
     stream = torch.cuda.Stream()
     ctx = N.Context(local_rank, stream.cuda_stream)
+    if os.environ.get("RG_APPLY_VARIANT"):
+        ctx.set_option("apply_variant", int(os.environ["RG_APPLY_VARIANT"]))
     if os.environ.get("RG_SORT_ROWS"):
         ctx.set_option("sort_rows", int(os.environ["RG_SORT_ROWS"]))
     if os.environ.get("RG_GROUP_WIDTH"):

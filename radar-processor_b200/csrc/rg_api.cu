@@ -138,6 +138,8 @@ void free_geometry(Geometry* g)
     cudaSetDevice(g->device);
     cudaFree(g->indptr);
     cudaFree(g->pairs);
+    cudaFree(g->sell);
+    cudaFree(g->slice_base);
     cudaFree(g->x_ax);
     cudaFree(g->y_ax);
     cudaFree(g->z_ax);
@@ -228,6 +230,16 @@ int make_product_params(const rg_grid_spec& gs, int n_products, const rg_product
         }
     }
     pp->any = n_products > 0 ? 1 : 0;
+    int words = 0;
+    pp->slot_cmax = pp->cmax_on ? words++ : -1;
+    pp->slot_cmin = pp->cmin_on ? words++ : -1;
+    pp->slot_cmean = pp->cmean_on ? words : -1;
+    if (pp->cmean_on) words += 2;
+    for (int k = 0; k < RG_MAX_SLICES; ++k) {
+        pp->slot_slice[k] = k < pp->n_slices ? words : -1;
+        if (k < pp->n_slices) words += 2;
+    }
+    pp->n_state_words = words;
     *z_need_lo = lo;
     *z_need_hi = hi;
     return RG_OK;
@@ -546,7 +558,10 @@ int rg_geometry_from_csr(rg_context* c, const rg_grid_spec* grid, const void* in
         if (st != RG_OK) return bail(st);
     }
     g->info.n_rows = n_rows; g->info.n_pairs = n_pairs; g->info.n_gates = n_gates; g->info.grid = *grid;
-    g->info.device_bytes = (int64_t)(((size_t)n_rows + 1) * 4 + (size_t)n_pairs * 8);
+    {
+        const int st = build_sell(ctx, g);
+        if (st != RG_OK) return bail(st);
+    }
     {
         const int st = finalize_geometry_stats(ctx, g);
         if (st != RG_OK) return bail(st);
@@ -837,6 +852,9 @@ int rg_apply(rg_context* c, const rg_geometry* geom, const rg_apply_args* a, int
     ap.pairs = g->pairs;
     ap.records = pk.records;
     ap.records_b = pk.records_b;
+    ap.sell = g->sell;
+    ap.slice_base = g->slice_base;
+    ap.slices_per_level = g->slices_per_level;
     ap.ncol = ncol;
     ap.nx = g->grid.nx;
     ap.ny = g->grid.ny;

@@ -195,6 +195,44 @@ struct ColumnState {
         }
     }
 
+    // Per-(field, column) words kept in shared memory by the thread-per-column kernel: word w of field f of
+    // thread t lives at sm[(w * n_fields + f) * blockDim.x + t].  zz[] is per column and stays in registers.
+    __device__ __forceinline__ void store_words(const ProductParams& pp, float* sm, int f, int n_fields) const
+    {
+        const int stride = blockDim.x, o = f * stride + threadIdx.x;
+        if (pp.slot_cmax >= 0) sm[pp.slot_cmax * n_fields * stride + o] = cmax;
+        if (pp.slot_cmin >= 0) sm[pp.slot_cmin * n_fields * stride + o] = cmin;
+        if (pp.slot_cmean >= 0) {
+            sm[pp.slot_cmean * n_fields * stride + o] = msum;
+            sm[(pp.slot_cmean + 1) * n_fields * stride + o] = __int_as_float(mcnt);
+        }
+#pragma unroll
+        for (int k = 0; k < RG_MAX_SLICES; ++k) {
+            if (pp.slot_slice[k] >= 0) {
+                sm[pp.slot_slice[k] * n_fields * stride + o] = s_lo[k];
+                sm[(pp.slot_slice[k] + 1) * n_fields * stride + o] = s_hi[k];
+            }
+        }
+    }
+
+    __device__ __forceinline__ void load_words(const ProductParams& pp, const float* sm, int f, int n_fields)
+    {
+        const int stride = blockDim.x, o = f * stride + threadIdx.x;
+        if (pp.slot_cmax >= 0) cmax = sm[pp.slot_cmax * n_fields * stride + o];
+        if (pp.slot_cmin >= 0) cmin = sm[pp.slot_cmin * n_fields * stride + o];
+        if (pp.slot_cmean >= 0) {
+            msum = sm[pp.slot_cmean * n_fields * stride + o];
+            mcnt = __float_as_int(sm[(pp.slot_cmean + 1) * n_fields * stride + o]);
+        }
+#pragma unroll
+        for (int k = 0; k < RG_MAX_SLICES; ++k) {
+            if (pp.slot_slice[k] >= 0) {
+                s_lo[k] = sm[pp.slot_slice[k] * n_fields * stride + o];
+                s_hi[k] = sm[(pp.slot_slice[k] + 1) * n_fields * stride + o];
+            }
+        }
+    }
+
     // planes are [field][ncol]
     __device__ __forceinline__ void write(const ProductParams& pp, int field, int64_t col, int64_t ncol, float x,
                                           float y) const
@@ -498,6 +536,140 @@ __global__ void __launch_bounds__(kApplyThreads) apply_columns_kernel(const __gr
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// K5  thread-per-column path over the interleaved ("sliced, compacted") copy of the table.
+//
+// A warp owns 32 consecutive columns, one per lane, and walks the levels bottom-up.  For one level the warp's 32
+// rows form a slice whose pairs are stored step-major (see rg_geometry.cu), so step k is ONE coalesced load of
+// the active lanes' k-th pairs; every lane then gathers its gate record and accumulates its own row in
+// registers.  No cross-lane reduction, no per-row shuffles, 32 rows share the per-level bookkeeping, and the
+// grid stores are 128-byte coalesced per field.  The pair addresses depend only on the row lengths, so several
+// steps are in flight before the first gather returns.  The few rows longer than kSellCap continue in the CSR
+// copy with the whole warp striding over the remainder.
+// ------------------------------------------------------------------------------------------------------
+template <int F, bool PROD>
+__global__ void __launch_bounds__(kSellThreads) apply_sell_kernel(const __grid_constant__ ApplyParams p)
+{
+    extern __shared__ float sm_state[];                        // [n_state_words][F][kSellThreads]
+    constexpr unsigned kFull = 0xFFFFFFFFu;
+    constexpr int NV = Layout<F>::NV;
+    constexpr int kDepth = 4;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int64_t col = (int64_t)blockIdx.x * kSellThreads + threadIdx.x;
+    const bool col_ok = col < p.ncol;
+    const int64_t slice_in_level = ((int64_t)blockIdx.x * kSellThreads + (threadIdx.x & ~31)) >> 5;
+
+    const uint32_t* __restrict__ indptr = p.indptr;
+    const uint2* __restrict__ sell = p.sell;
+    const float* __restrict__ rec = p.records;
+    const float* __restrict__ rec_b = p.records_b;
+
+    float x = 0.f, y = 0.f;
+    ColumnState st;
+    if constexpr (PROD) {
+        if (col_ok) {
+            x = __ldg(p.prod.x_ax + (int)(col % p.nx));
+            y = __ldg(p.prod.y_ax + (int)(col / p.nx));
+        }
+        st.init(p.prod, x, y);
+#pragma unroll
+        for (int f = 0; f < F; ++f) st.store_words(p.prod, sm_state, f, F);
+    }
+
+    uint32_t s_next = 0, e_next = 0;
+    if (col_ok && p.lz_first < p.lz_last) {
+        const size_t row = (size_t)p.lz_first * (size_t)p.ncol + (size_t)col;
+        s_next = __ldg(indptr + row);
+        e_next = __ldg(indptr + row + 1);
+    }
+
+    for (int lz = p.lz_first; lz < p.lz_last; ++lz) {
+        const uint32_t s = s_next, e = e_next;
+        const size_t row = (size_t)lz * (size_t)p.ncol + (size_t)col;
+        if (col_ok && lz + 1 < p.lz_last) {
+            s_next = __ldg(indptr + row + (size_t)p.ncol);
+            e_next = __ldg(indptr + row + (size_t)p.ncol + 1);
+        }
+        const uint32_t len = e - s;
+        const uint32_t n = min(len, kSellCap);
+        uint32_t base = __ldg(p.slice_base + (size_t)lz * (size_t)p.slices_per_level + (size_t)slice_in_level);
+        const uint32_t kmax = __reduce_max_sync(kFull, n);
+
+        float swv[F], sw[F];
+#pragma unroll
+        for (int f = 0; f < F; ++f) { swv[f] = 0.f; sw[f] = 0.f; }
+
+        for (uint32_t k = 0; k < kmax; k += kDepth) {
+            uint32_t addr[kDepth];
+            bool act[kDepth];
+#pragma unroll
+            for (int j = 0; j < kDepth; ++j) {
+                act[j] = k + j < n;
+                const unsigned m = __ballot_sync(kFull, act[j]);
+                addr[j] = base + __popc(m & lt_mask);
+                base += __popc(m);
+            }
+            uint2 pr[kDepth];
+#pragma unroll
+            for (int j = 0; j < kDepth; ++j) pr[j] = act[j] ? __ldcs(sell + addr[j]) : make_uint2(0u, 0u);
+            float v[kDepth][NV];
+#pragma unroll
+            for (int j = 0; j < kDepth; ++j)
+                if (act[j]) load_record<F>(rec, rec_b, pr[j].x, v[j]);
+#pragma unroll
+            for (int j = 0; j < kDepth; ++j)
+                if (act[j]) accumulate<F, NV>(__uint_as_float(pr[j].y), v[j], swv, sw);
+        }
+
+        // rows longer than the interleaved copy holds: the whole warp strides over the rest in the CSR copy
+        unsigned heavy = __ballot_sync(kFull, len > kSellCap);
+        while (heavy) {
+            const int src = __ffs(heavy) - 1;
+            heavy &= heavy - 1;
+            const uint32_t hs = __shfl_sync(kFull, s, src) + kSellCap;
+            const uint32_t he = __shfl_sync(kFull, e, src);
+            float hwv[F], hw[F];
+#pragma unroll
+            for (int f = 0; f < F; ++f) { hwv[f] = 0.f; hw[f] = 0.f; }
+            gather_run<F>(p.pairs, rec, rec_b, hs + lane, he, 32, hwv, hw);
+#pragma unroll
+            for (int f = 0; f < F; ++f) {
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    hwv[f] += __shfl_xor_sync(kFull, hwv[f], off);
+                    hw[f] += __shfl_xor_sync(kFull, hw[f], off);
+                }
+                if (lane == src) { swv[f] += hwv[f]; sw[f] += hw[f]; }
+            }
+        }
+
+        if (col_ok) {
+#pragma unroll
+            for (int f = 0; f < F; ++f) {
+                const float val = sw[f] > 0.f ? __fdiv_rn(swv[f], sw[f]) : p.fill;   // interpolate.py:99-102
+                float* out = p.grid_out[f];
+                if (out != nullptr) __stcs(out + row, val);
+                if constexpr (PROD) {
+                    st.load_words(p.prod, sm_state, f, F);
+                    st.update(p.prod, p.z_begin + lz, val);
+                    st.store_words(p.prod, sm_state, f, F);
+                }
+            }
+        }
+    }
+
+    if constexpr (PROD) {
+        if (col_ok) {
+#pragma unroll
+            for (int f = 0; f < F; ++f) {
+                st.load_words(p.prod, sm_state, f, F);
+                st.write(p.prod, f, col, p.ncol, x, y);
+            }
+        }
+    }
+}
+
 #if RG_VAR == 3
 // Lane-paired variant (32-byte records, F >= 5, 8 lanes per column = 4 slots x 2 halves).
 // Slot q of a group handles two consecutive pairs per step; lane h of the slot loads half h (fields 4h..4h+3)
@@ -794,6 +966,21 @@ static int launch_columns_w(Context* ctx, const ApplyParams& p, int W)
     return RG_OK;
 }
 
+template <int F>
+static int launch_sell(Context* ctx, const ApplyParams& p)
+{
+    const unsigned blocks = (unsigned)((p.ncol + kSellThreads - 1) / kSellThreads);
+    const size_t smem = p.prod.any ? (size_t)p.prod.n_state_words * F * kSellThreads * sizeof(float) : 0;
+    if (p.prod.any) {
+        if (smem > 48 * 1024)
+            RG_CUDA(cudaFuncSetAttribute(apply_sell_kernel<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        apply_sell_kernel<F, true><<<blocks, kSellThreads, smem, ctx->stream>>>(p);
+    } else {
+        apply_sell_kernel<F, false><<<blocks, kSellThreads, 0, ctx->stream>>>(p);
+    }
+    return RG_OK;
+}
+
 static int pick_group_width(const Context* ctx, const Geometry* g, int n_fields)
 {
     int W = (int)ctx->group_width;
@@ -819,6 +1006,26 @@ int launch_apply(Context* ctx, const Geometry* g, const ApplyParams& p, bool ref
             default: apply_reference_order_kernel<8><<<blocks, 128, 0, ctx->stream>>>(p, g->n_rows); break;
         }
         ctx->launches++;
+        RG_CUDA(cudaGetLastError());
+        return RG_OK;
+    }
+    if (ctx->apply_variant != 1) {                      // default: thread-per-column over the interleaved copy
+        timer_begin(ctx, kTimerApply);
+        int st = RG_OK;
+        switch (p.n_fields) {
+            case 1: st = launch_sell<1>(ctx, p); break;
+            case 2: st = launch_sell<2>(ctx, p); break;
+            case 3: st = launch_sell<3>(ctx, p); break;
+            case 4: st = launch_sell<4>(ctx, p); break;
+            case 5: st = launch_sell<5>(ctx, p); break;
+            case 6: st = launch_sell<6>(ctx, p); break;
+            case 7: st = launch_sell<7>(ctx, p); break;
+            case 8: st = launch_sell<8>(ctx, p); break;
+            default: return fail(RG_ERR_INVALID, "n_fields must be 1..8");
+        }
+        timer_end(ctx, kTimerApply);
+        ctx->launches++;
+        RG_TRY(st);
         RG_CUDA(cudaGetLastError());
         return RG_OK;
     }

@@ -220,6 +220,8 @@ __global__ void scan_write_total_kernel(const unsigned long long* total, uint32_
     *out_last = (uint32_t)(*total);
 }
 
+}  // namespace
+
 // out[0..n] = exclusive scan of in[0..n-1]; *total_host = sum.  `tmp` must hold ceil(n/4096)+1 u64.
 int exclusive_scan_u32(Context* ctx, const uint32_t* in, uint32_t* out, int64_t n, unsigned long long* tmp,
                        uint64_t* total_host)
@@ -245,6 +247,8 @@ int exclusive_scan_u32(Context* ctx, const uint32_t* in, uint32_t* out, int64_t 
     *total_host = t;
     return RG_OK;
 }
+
+namespace {
 
 // ---- K2 / K3: warp-per-voxel neighbour search -----------------------------------------------------------
 struct NeighbourParams {
@@ -438,6 +442,55 @@ __global__ void __launch_bounds__(256) row_stats_kernel(const uint32_t* __restri
     }
 }
 
+// ---- interleaved copy of the table for the thread-per-column apply kernel ---------------------------------
+// A slice = 32 consecutive columns of one level = 32 consecutive CSR rows.  Inside a slice the pairs are stored
+// step-major: all rows' element 0, then all rows' element 1, ... with rows that have run out simply skipped, so
+// lane r of a warp reads element k of row r at  base + sum_{k'<k} active(k') + rank_k(r)  — the active lanes of
+// every step read consecutive addresses (perfectly coalesced), nothing is padded, and the copy holds exactly
+// sum(min(len, kSellCap)) pairs.
+__global__ void __launch_bounds__(128) sell_count_kernel(const uint32_t* __restrict__ indptr, int64_t ncol, int n_levels,
+                                                         int64_t slices_per_level, uint32_t* __restrict__ slice_count)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t slice = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (slice >= slices_per_level * n_levels) return;
+    const int64_t lz = slice / slices_per_level, sb = slice - lz * slices_per_level;
+    const int64_t col = sb * 32 + lane;
+    uint32_t n = 0;
+    if (col < ncol) {
+        const size_t row = (size_t)lz * (size_t)ncol + (size_t)col;
+        n = min(indptr[row + 1] - indptr[row], kSellCap);
+    }
+    for (int off = 16; off >= 1; off >>= 1) n += __shfl_xor_sync(0xFFFFFFFFu, n, off);
+    if (lane == 0) slice_count[slice] = n;
+}
+
+__global__ void __launch_bounds__(128) sell_fill_kernel(const uint32_t* __restrict__ indptr, const uint2* __restrict__ pairs,
+                                                        int64_t ncol, int n_levels, int64_t slices_per_level,
+                                                        const uint32_t* __restrict__ slice_base, uint2* __restrict__ sell)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int64_t slice = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (slice >= slices_per_level * n_levels) return;
+    const int64_t lz = slice / slices_per_level, sb = slice - lz * slices_per_level;
+    const int64_t col = sb * 32 + lane;
+    uint32_t s = 0, n = 0;
+    if (col < ncol) {
+        const size_t row = (size_t)lz * (size_t)ncol + (size_t)col;
+        s = indptr[row];
+        n = min(indptr[row + 1] - s, kSellCap);
+    }
+    uint32_t base = slice_base[slice];
+    const uint32_t kmax = __reduce_max_sync(0xFFFFFFFFu, n);
+    for (uint32_t k = 0; k < kmax; ++k) {
+        const bool act = k < n;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, act);
+        if (act) sell[base + __popc(m & lt_mask)] = pairs[s + k];
+        base += __popc(m);
+    }
+}
+
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
@@ -465,6 +518,38 @@ void linspace_f32(double start, double stop, int num, float* out)
     } else {
         out[0] = (float)(0.0 * delta + start);
     }
+}
+
+int build_sell(Context* ctx, Geometry* g)
+{
+    g->slices_per_level = (g->ncol + 31) / 32;
+    const int64_t n_slices = g->slices_per_level * g->n_levels;
+    if (g->sell) { cudaFree(g->sell); g->sell = nullptr; }
+    if (g->slice_base) { cudaFree(g->slice_base); g->slice_base = nullptr; }
+    RG_CUDA(cudaMalloc(&g->slice_base, ((size_t)n_slices + 1) * sizeof(uint32_t)));
+    DevBuf<uint32_t> counts;
+    DevBuf<unsigned long long> tmp;
+    RG_CUDA(counts.alloc((size_t)n_slices));
+    RG_CUDA(tmp.alloc((size_t)(n_slices / kScanTile + 4)));
+    const unsigned blocks = (unsigned)((n_slices + 3) / 4);
+    if (n_slices > 0) {
+        sell_count_kernel<<<blocks, 128, 0, ctx->stream>>>(g->indptr, g->ncol, g->n_levels, g->slices_per_level, counts.p);
+        ctx->launches++;
+        RG_CUDA(cudaGetLastError());
+    }
+    uint64_t total = 0;
+    RG_TRY(exclusive_scan_u32(ctx, counts.p, g->slice_base, n_slices, tmp.p, &total));
+    g->n_sell = (int64_t)total;
+    RG_CUDA(cudaMalloc(&g->sell, std::max<size_t>((size_t)total, 1) * sizeof(uint2)));
+    if (n_slices > 0 && total > 0) {
+        sell_fill_kernel<<<blocks, 128, 0, ctx->stream>>>(g->indptr, g->pairs, g->ncol, g->n_levels, g->slices_per_level,
+                                                         g->slice_base, g->sell);
+        ctx->launches++;
+        RG_CUDA(cudaGetLastError());
+    }
+    RG_CUDA(cudaStreamSynchronize(ctx->stream));
+    g->info.device_bytes = (int64_t)(((size_t)g->n_rows + 1) * 4 + (size_t)g->n_pairs * 8 + (size_t)total * 8 + ((size_t)n_slices + 1) * 4);
+    return RG_OK;
 }
 
 int finalize_geometry_stats(Context* ctx, Geometry* g)
@@ -624,6 +709,8 @@ int build_geometry_device(Context* ctx, const float* gx, const float* gy, const 
         ctx->launches++;
         RG_CUDA(cudaGetLastError());
     }
+    out->n_rows = n_rows; out->n_pairs = (int64_t)n_pairs; out->ncol = ncol; out->n_levels = n_levels;
+    RG_TRY(build_sell(ctx, out));
     RG_CUDA(cudaEventRecord(ev1, ctx->stream));
     RG_CUDA(cudaStreamSynchronize(ctx->stream));
     float ms = 0.f;
@@ -637,7 +724,6 @@ int build_geometry_device(Context* ctx, const float* gx, const float* gy, const 
     out->info.n_rows = n_rows; out->info.n_pairs = (int64_t)n_pairs; out->info.n_gates = n_gates;
     out->info.n_gates_binned = (int64_t)n_binned; out->info.n_candidates = (int64_t)cand;
     out->info.build_ms = ms; out->info.cell_size = cell; out->info.grid = gs;
-    out->info.device_bytes = (int64_t)(((size_t)n_rows + 1) * 4 + (size_t)n_pairs * 8);
     return finalize_geometry_stats(ctx, out);
 }
 

@@ -9,7 +9,7 @@
 #include "radar_grid_b200.h"
 
 #ifndef RG_VAR
-#define RG_VAR 1          // gate-record layout / accumulate variant of the apply kernel, see rg_apply.cu
+#define RG_VAR 2          // gate-record layout / accumulate variant of the apply kernel, see rg_apply.cu
 #endif
 
 namespace rg {
@@ -42,6 +42,8 @@ constexpr uint32_t kInvalidCell = 0xFFFFFFFFu;
 
 constexpr int kApplyThreads = 256;       // threads per CTA of the column-tile apply kernel
 constexpr uint32_t kHeavyRow = 512;      // rows longer than this are reduced by the whole warp
+constexpr int kSellThreads = 128;        // threads per CTA of the thread-per-column apply kernel
+constexpr uint32_t kSellCap = 192;       // pairs of a row kept in the interleaved copy; the rest is read from the CSR
 
 // Device-resident neighbour table of one z-slab.
 struct Geometry {
@@ -51,6 +53,10 @@ struct Geometry {
     int32_t n_levels = 0;
     uint32_t* indptr = nullptr;          // [n_rows + 1]
     uint2* pairs = nullptr;              // [n_pairs] {gate id, float32 weight bits}
+    // Sliced, lane-interleaved, compacted copy of the first kSellCap pairs of every row (see rg_apply.cu):
+    uint2* sell = nullptr;               // [n_sell]
+    uint32_t* slice_base = nullptr;      // [n_levels * slices_per_level + 1]
+    int64_t n_sell = 0, slices_per_level = 0;
     float* x_ax = nullptr;               // [nx]   float32 linspace axes (reference compute.py:184-186)
     float* y_ax = nullptr;               // [ny]
     float* z_ax = nullptr;               // [nz]   (full grid)
@@ -116,6 +122,9 @@ struct ProductParams {
     const float* x_ax;
     const float* y_ax;
     SliceParams slices[RG_MAX_SLICES];
+    // shared-memory slots of the per-(field, column) product state in the thread-per-column kernel (-1 = unused)
+    int32_t n_state_words;
+    int32_t slot_cmax, slot_cmin, slot_cmean, slot_slice[RG_MAX_SLICES];
 };
 
 struct ApplyParams {
@@ -123,6 +132,9 @@ struct ApplyParams {
     const uint2* pairs;
     const float* records;                 // [n_gates][FP]  (RG_VAR 2: fields 0..3)
     const float* records_b;               // RG_VAR 2: fields 4..7
+    const uint2* sell;                    // interleaved copy of the table (thread-per-column kernel)
+    const uint32_t* slice_base;
+    int64_t slices_per_level;
     int64_t ncol;                         // ny*nx
     int32_t nx, ny;
     int32_t z_begin;                      // global index of local level 0
@@ -159,6 +171,8 @@ int build_geometry_device(Context* ctx, const float* gx, const float* gy, const 
                           double radar_altitude, double min_radius, double beam_factor, int weighting,
                           double toa, Geometry* out);
 int finalize_geometry_stats(Context* ctx, Geometry* g);
+int build_sell(Context* ctx, Geometry* g);
+int exclusive_scan_u32(Context* ctx, const uint32_t* in, uint32_t* out, int64_t n, unsigned long long* tmp, uint64_t* total_host);
 void linspace_f32(double start, double stop, int num, float* out);
 
 }  // namespace rg

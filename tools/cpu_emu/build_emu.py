@@ -69,7 +69,8 @@ def rewrite_launches(src: str) -> str:
             q += 1
         args = src[p + 1:q].strip()
         out.append(src[i:k])
-        out.append(f"emu_launch({name}, dim3({parts[0].strip()}), dim3({parts[1].strip()})" + (", " + args if args else "") + ")")
+        smem = parts[2].strip() if len(parts) > 2 else "0"
+        out.append(f"emu_launch({name}, dim3({parts[0].strip()}), dim3({parts[1].strip()}), (size_t)({smem})" + (", " + args if args else "") + ")")
         i = q + 1
     return "".join(out)
 
@@ -80,7 +81,9 @@ def main():
     for f in ("rg_api.cu", "rg_apply.cu", "rg_geometry.cu"):
         src = open(os.path.join(CSRC, f)).read()
         dst = os.path.join(OUT, f.replace(".cu", ".cpp"))
-        open(dst, "w").write(rewrite_launches(src))
+        text = rewrite_launches(src)
+        text = re.sub(r"extern\s+__shared__\s+(\w+)\s+(\w+)\[\];", r"\1* \2 = (\1*)emu_dynamic_smem;", text)
+        open(dst, "w").write(text)
         cpps.append(dst)
     lib = os.path.join(OUT, "libradargrid_b200_emu.so")
     cmd = ["g++", "-std=c++20", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-Wno-unknown-pragmas", *os.environ.get("RG_EMU_FLAGS", "").split(),

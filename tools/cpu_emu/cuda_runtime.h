@@ -107,6 +107,8 @@ inline double __dsqrt_rn(double a) { return sqrt(a); }
 inline float __double2float_rn(double a) { return (float)a; }
 inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
+inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 template <typename T> inline T __ldg(const T* p) { return *p; }
@@ -124,9 +126,13 @@ inline unsigned atomicMax(unsigned* p, unsigned v)
 }
 
 // ---- launch ---------------------------------------------------------------------------------------------
+inline void* emu_dynamic_smem = nullptr;
+
 template <typename K, typename... A>
-inline void emu_launch(K kernel, dim3 grid, dim3 block, A... args)
+inline void emu_launch(K kernel, dim3 grid, dim3 block, size_t smem_bytes, A... args)
 {
+    std::vector<char> dyn(smem_bytes + 16);
+    emu_dynamic_smem = dyn.data();
     const unsigned nthreads = block.x * block.y * block.z;
     const unsigned nwarps = (nthreads + 31) / 32;
     const uint64_t nblocks = (uint64_t)grid.x * grid.y * grid.z;
@@ -172,6 +178,8 @@ enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2 };
 typedef void* cudaStream_t;
 typedef void* cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <typename K> inline cudaError_t cudaFuncSetAttribute(K, int, int) { return cudaSuccess; }
 enum { cudaStreamNonBlocking = 1, cudaHostAllocDefault = 0, cudaDevAttrMultiProcessorCount = 16 };
 inline const char* cudaGetErrorString(cudaError_t) { return "emulated CUDA error"; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
