@@ -814,7 +814,7 @@ int rg_apply(rg_context* c, const rg_geometry* geom, const rg_apply_args* a, int
         pk.rule_use_lo[r] = q.use_lo; pk.rule_use_hi[r] = q.use_hi;
         pk.rule_bits[r] = q.field_bits;
     }
-    RG_TRY(ensure(ctx, ctx->records, std::max<size_t>((size_t)G * FP * 4, 16) + 512));
+    RG_TRY(ensure(ctx, ctx->records, (size_t)(G + 1) * FP * 4 + 1024));
     pk.records = (float*)ctx->records.ptr;
     pk.records_b = (float*)((char*)ctx->records.ptr + records_b_offset(F, G));
     RG_TRY(launch_pack(ctx, pk));
@@ -855,6 +855,7 @@ int rg_apply(rg_context* c, const rg_geometry* geom, const rg_apply_args* a, int
     ap.sell = g->sell;
     ap.slice_base = g->slice_base;
     ap.slices_per_level = g->slices_per_level;
+    ap.null_gate = (uint32_t)G;
     ap.ncol = ncol;
     ap.nx = g->grid.nx;
     ap.ny = g->grid.ny;

@@ -40,11 +40,12 @@ __global__ void __launch_bounds__(256) pack_records_kernel(const __grid_constant
     // FB == 0: one AoS array of FA floats per gate.  FB > 0 (RG_VAR 2): fields 0..FA-1 in array A, FA.. in array B.
     constexpr int NV = FA + FB;
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= p.n_gates) return;
+    if (g > p.n_gates) return;
+    const bool null_gate = g == p.n_gates;       // record n_gates is all-masked: a harmless target for idle lanes
 
     // one exclusion bit per field from the fused range rules (filters.py:133-134, 156-157, 208-209)
     uint32_t excluded = 0;
-    for (int r = 0; r < p.n_rules; ++r) {
+    for (int r = 0; r < p.n_rules && !null_gate; ++r) {
         const float q = __ldg(p.rule_values[r] + g);
         const bool hit = (p.rule_use_lo[r] && q < p.rule_lo[r]) || (p.rule_use_hi[r] && q > p.rule_hi[r]);
         if (hit) excluded |= p.rule_bits[r];
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__(256) pack_records_kernel(const __grid_constant
 #pragma unroll
     for (int f = 0; f < NV; ++f) {
         uint32_t bits = kMaskedBits;
-        if (f < p.n_fields) {
+        if (f < p.n_fields && !null_gate) {
             const float v = __ldg(p.fields[f] + g);
             bool masked = (excluded >> f) & 1u;
             if (p.masks[f] != nullptr) masked |= __ldg(p.masks[f] + g) != 0;
@@ -82,13 +83,12 @@ int records_width(int n_fields) { return n_fields <= 1 ? 1 : n_fields == 2 ? 2 :
 size_t records_b_offset(int n_fields, int64_t n_gates)
 {
     const int fa = n_fields == 1 ? 1 : n_fields == 2 ? 2 : 4;
-    return (((size_t)n_gates * fa * sizeof(float)) + 255) & ~(size_t)255;
+    return (((size_t)(n_gates + 1) * fa * sizeof(float)) + 255) & ~(size_t)255;
 }
 
 int launch_pack(Context* ctx, const PackParams& p)
 {
-    if (p.n_gates == 0) return RG_OK;
-    const unsigned blocks = (unsigned)((p.n_gates + 255) / 256);
+    const unsigned blocks = (unsigned)((p.n_gates + 1 + 255) / 256);
     timer_begin(ctx, kTimerPack);
 #if RG_VAR == 2
     switch (p.n_fields) {
@@ -152,7 +152,7 @@ struct ColumnState {
 #pragma unroll
         for (int k = 0; k < RG_MAX_SLICES; ++k) {
             s_lo[k] = s_hi[k] = __uint_as_float(kCanonNaN);
-            zz[k] = 0;
+            zz[k] = 0x7FFF7FFF;          // unused slice: a level no grid has (nz <= 32767)
             if (k < pp.n_slices) {
                 const SliceParams& s = pp.slices[k];
                 int lo, hi;
@@ -188,10 +188,8 @@ struct ColumnState {
         }
 #pragma unroll
         for (int k = 0; k < RG_MAX_SLICES; ++k) {
-            if (k < pp.n_slices) {
-                if (z == (zz[k] & 0xFFFF)) s_lo[k] = v;
-                if (z == (zz[k] >> 16)) s_hi[k] = v;
-            }
+            if (z == (zz[k] & 0xFFFF)) s_lo[k] = v;
+            if (z == (zz[k] >> 16)) s_hi[k] = v;
         }
     }
 
@@ -333,6 +331,72 @@ int launch_products(Context* ctx, const rg_grid_spec& grid, int n_fields, const 
 //   3  AoS 32 B, two lanes per record: lane h of a pair loads half h (16 B) of two consecutive pairs'
 //      records, so one load instruction touches each 128-byte line once instead of twice
 // ------------------------------------------------------------------------------------------------------
+#ifndef RG_PREFETCH
+#define RG_PREFETCH 1          // levels of look-ahead for the L2 prefetch of the pair stream (0 = off)
+#endif
+#ifndef RG_TREDUCE
+#define RG_TREDUCE 1           // 1: reduce-scatter the row sums inside a group (14 shuffles), 0: plain butterfly (6F)
+#endif
+#ifndef RG_UNROLL
+#define RG_UNROLL 4            // pairs (and their gathers) in flight per lane
+#endif
+#ifndef RG_MINBLOCKS
+#define RG_MINBLOCKS 1
+#endif
+
+__device__ __forceinline__ void prefetch_l2(const void* ptr)
+{
+#ifndef RG_EMU
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+#else
+    (void)ptr;
+#endif
+}
+
+// Reduce-scatter of F (sum_wv, sum_w) units over the 8 lanes of a group: three halving exchanges
+// (4 + 2 + 1 units) instead of a full butterfly per value; lane g ends up with the totals of field g.
+template <int F>
+__device__ __forceinline__ void group8_reduce_scatter(const float (&swv)[F], const float (&sw)[F], int gl, float& a, float& b)
+{
+    constexpr unsigned kFull = 0xFFFFFFFFu;
+    float u_wv[8], u_w[8];
+#pragma unroll
+    for (int f = 0; f < 8; ++f) { u_wv[f] = f < F ? swv[f] : 0.f; u_w[f] = f < F ? sw[f] : 0.f; }
+    float t_wv[4], t_w[4];
+    {
+        const bool up = gl & 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j < F) {                       // fields j and j+4 take part only if they exist
+                const float send_wv = up ? u_wv[j] : u_wv[j + 4];
+                const float send_w = up ? u_w[j] : u_w[j + 4];
+                t_wv[j] = (up ? u_wv[j + 4] : u_wv[j]) + __shfl_xor_sync(kFull, send_wv, 4);
+                t_w[j] = (up ? u_w[j + 4] : u_w[j]) + __shfl_xor_sync(kFull, send_w, 4);
+            } else {
+                t_wv[j] = 0.f; t_w[j] = 0.f;
+            }
+        }
+    }
+    float s_wv[2], s_w[2];
+    {
+        const bool up = gl & 2;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if (j < F) {
+                const float send_wv = up ? t_wv[j] : t_wv[j + 2];
+                const float send_w = up ? t_w[j] : t_w[j + 2];
+                s_wv[j] = (up ? t_wv[j + 2] : t_wv[j]) + __shfl_xor_sync(kFull, send_wv, 2);
+                s_w[j] = (up ? t_w[j + 2] : t_w[j]) + __shfl_xor_sync(kFull, send_w, 2);
+            } else {
+                s_wv[j] = 0.f; s_w[j] = 0.f;
+            }
+        }
+    }
+    const bool up = gl & 1;
+    a = (up ? s_wv[1] : s_wv[0]) + __shfl_xor_sync(kFull, up ? s_wv[0] : s_wv[1], 1);
+    b = (up ? s_w[1] : s_w[0]) + __shfl_xor_sync(kFull, up ? s_w[0] : s_w[1], 1);
+}
+
 template <int F>
 struct Layout {
     static constexpr int FP = F == 1 ? 1 : F == 2 ? 2 : F <= 4 ? 4 : 8;
@@ -397,28 +461,24 @@ __device__ __forceinline__ void accumulate(float w, const float (&v)[NV], float 
     }
 }
 
-// Sum pairs [p, e) with stride `step`, four pairs (and their gathers) in flight per lane.
+// Sum pairs [p, e) with stride `step`, RG_UNROLL pairs (and their gathers) in flight per lane.
 template <int F>
 __device__ __forceinline__ void gather_run(const uint2* __restrict__ pairs, const float* __restrict__ rec,
                                            const float* __restrict__ rec_b, uint32_t p, uint32_t e, uint32_t step,
                                            float (&swv)[F], float (&sw)[F])
 {
     constexpr int NV = Layout<F>::NV;
-    while (p < e && e - p > 3 * step) {
-        const uint2 a0 = __ldcs(pairs + p);
-        const uint2 a1 = __ldcs(pairs + p + step);
-        const uint2 a2 = __ldcs(pairs + p + 2 * step);
-        const uint2 a3 = __ldcs(pairs + p + 3 * step);
-        float v0[NV], v1[NV], v2[NV], v3[NV];
-        load_record<F>(rec, rec_b, a0.x, v0);
-        load_record<F>(rec, rec_b, a1.x, v1);
-        load_record<F>(rec, rec_b, a2.x, v2);
-        load_record<F>(rec, rec_b, a3.x, v3);
-        accumulate<F, NV>(__uint_as_float(a0.y), v0, swv, sw);
-        accumulate<F, NV>(__uint_as_float(a1.y), v1, swv, sw);
-        accumulate<F, NV>(__uint_as_float(a2.y), v2, swv, sw);
-        accumulate<F, NV>(__uint_as_float(a3.y), v3, swv, sw);
-        p += 4 * step;
+    constexpr int U = RG_UNROLL;
+    while (p < e && e - p > (U - 1) * step) {
+        uint2 a[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) a[j] = __ldcs(pairs + p + j * step);
+        float v[U][NV];
+#pragma unroll
+        for (int j = 0; j < U; ++j) load_record<F>(rec, rec_b, a[j].x, v[j]);
+#pragma unroll
+        for (int j = 0; j < U; ++j) accumulate<F, NV>(__uint_as_float(a[j].y), v[j], swv, sw);
+        p += U * step;
     }
     while (p < e) {
         const uint2 a0 = __ldcs(pairs + p);
@@ -430,7 +490,7 @@ __device__ __forceinline__ void gather_run(const uint2* __restrict__ pairs, cons
 }
 
 template <int F, int W, bool PROD>
-__global__ void __launch_bounds__(kApplyThreads) apply_columns_kernel(const __grid_constant__ ApplyParams p)
+__global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_kernel(const __grid_constant__ ApplyParams p)
 {
     static_assert(W >= F || W == 32, "one lane per field in the epilogue");
     constexpr unsigned kFull = 0xFFFFFFFFu;
@@ -469,6 +529,16 @@ __global__ void __launch_bounds__(kApplyThreads) apply_columns_kernel(const __gr
             s_next = __ldg(indptr + row + (size_t)p.ncol);
             e_next = __ldg(indptr + row + (size_t)p.ncol + 1);
         }
+#if RG_PREFETCH > 0
+        // Pull the pair lines of the row RG_PREFETCH levels up from HBM into L2 now: by the time this group
+        // gets there the stream load is an L2 hit.  One 128-byte line per lane, lanes of the group side by side.
+        if (col_ok && lz + RG_PREFETCH < p.lz_last) {
+            const size_t prow = row + (size_t)RG_PREFETCH * (size_t)p.ncol;
+            const uint32_t ps = RG_PREFETCH == 1 ? s_next : __ldg(indptr + prow);
+            const uint32_t pe = RG_PREFETCH == 1 ? e_next : __ldg(indptr + prow + 1);
+            for (uint32_t q = ps + 16u * gl; q < pe; q += 16u * W) prefetch_l2(pairs + q);
+        }
+#endif
 
         float swv[F], sw[F];
 #pragma unroll
@@ -508,20 +578,32 @@ __global__ void __launch_bounds__(kApplyThreads) apply_columns_kernel(const __gr
 
         if (!heavy_mine) gather_run<F>(pairs, rec, rec_b, s + gl, e, W, swv, sw);
 
-        // butterfly inside the group: afterwards every lane of the group holds the row sums
-#pragma unroll
-        for (int f = 0; f < F; ++f) {
-#pragma unroll
-            for (int off = W / 2; off >= 1; off >>= 1) {
-                swv[f] += __shfl_xor_sync(kFull, swv[f], off);
-                sw[f] += __shfl_xor_sync(kFull, sw[f], off);
-            }
-        }
-
         float a = 0.f, b = 0.f;
+        if constexpr (RG_TREDUCE && W >= 8) {
+            // plain butterfly down to 8 lanes, then reduce-scatter: lane f of the group gets field f
 #pragma unroll
-        for (int f = 0; f < F; ++f)
-            if (gl == f) { a = swv[f]; b = sw[f]; }
+            for (int f = 0; f < F; ++f) {
+#pragma unroll
+                for (int off = W / 2; off >= 8; off >>= 1) {
+                    swv[f] += __shfl_xor_sync(kFull, swv[f], off);
+                    sw[f] += __shfl_xor_sync(kFull, sw[f], off);
+                }
+            }
+            group8_reduce_scatter<F>(swv, sw, gl & 7, a, b);
+        } else {
+            // butterfly inside the group: afterwards every lane of the group holds the row sums
+#pragma unroll
+            for (int f = 0; f < F; ++f) {
+#pragma unroll
+                for (int off = W / 2; off >= 1; off >>= 1) {
+                    swv[f] += __shfl_xor_sync(kFull, swv[f], off);
+                    sw[f] += __shfl_xor_sync(kFull, sw[f], off);
+                }
+            }
+#pragma unroll
+            for (int f = 0; f < F; ++f)
+                if (gl == f) { a = swv[f]; b = sw[f]; }
+        }
 
         if (owner) {
             const float v = b > 0.f ? __fdiv_rn(a, b) : p.fill;            // interpolate.py:99-102
@@ -593,8 +675,16 @@ __global__ void __launch_bounds__(kSellThreads) apply_sell_kernel(const __grid_c
         }
         const uint32_t len = e - s;
         const uint32_t n = min(len, kSellCap);
-        uint32_t base = __ldg(p.slice_base + (size_t)lz * (size_t)p.slices_per_level + (size_t)slice_in_level);
+        const uint32_t* sbp = p.slice_base + (size_t)lz * (size_t)p.slices_per_level + (size_t)slice_in_level;
+        uint32_t base = __ldg(sbp);
         const uint32_t kmax = __reduce_max_sync(kFull, n);
+#if RG_PREFETCH > 0
+        if (lz + RG_PREFETCH < p.lz_last) {                   // next level's slice: HBM -> L2 while this one is summed
+            const uint32_t b0 = __ldg(sbp + (size_t)RG_PREFETCH * (size_t)p.slices_per_level);
+            const uint32_t b1 = __ldg(sbp + (size_t)RG_PREFETCH * (size_t)p.slices_per_level + 1);
+            for (uint32_t q = b0 + 16u * lane; q < b1; q += 16u * 32u) prefetch_l2(sell + q);
+        }
+#endif
 
         float swv[F], sw[F];
 #pragma unroll
@@ -610,16 +700,15 @@ __global__ void __launch_bounds__(kSellThreads) apply_sell_kernel(const __grid_c
                 addr[j] = base + __popc(m & lt_mask);
                 base += __popc(m);
             }
+            // idle lanes point at the all-masked record n_gates: no divergent control flow in the hot loop
             uint2 pr[kDepth];
 #pragma unroll
-            for (int j = 0; j < kDepth; ++j) pr[j] = act[j] ? __ldcs(sell + addr[j]) : make_uint2(0u, 0u);
+            for (int j = 0; j < kDepth; ++j) pr[j] = act[j] ? __ldcs(sell + addr[j]) : make_uint2(p.null_gate, 0u);
             float v[kDepth][NV];
 #pragma unroll
-            for (int j = 0; j < kDepth; ++j)
-                if (act[j]) load_record<F>(rec, rec_b, pr[j].x, v[j]);
+            for (int j = 0; j < kDepth; ++j) load_record<F>(rec, rec_b, pr[j].x, v[j]);
 #pragma unroll
-            for (int j = 0; j < kDepth; ++j)
-                if (act[j]) accumulate<F, NV>(__uint_as_float(pr[j].y), v[j], swv, sw);
+            for (int j = 0; j < kDepth; ++j) accumulate<F, NV>(__uint_as_float(pr[j].y), v[j], swv, sw);
         }
 
         // rows longer than the interleaved copy holds: the whole warp strides over the rest in the CSR copy

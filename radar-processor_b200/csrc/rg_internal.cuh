@@ -42,7 +42,7 @@ constexpr uint32_t kInvalidCell = 0xFFFFFFFFu;
 
 constexpr int kApplyThreads = 256;       // threads per CTA of the column-tile apply kernel
 constexpr uint32_t kHeavyRow = 512;      // rows longer than this are reduced by the whole warp
-constexpr int kSellThreads = 128;        // threads per CTA of the thread-per-column apply kernel
+constexpr int kSellThreads = 64;         // threads per CTA of the thread-per-column apply kernel
 constexpr uint32_t kSellCap = 192;       // pairs of a row kept in the interleaved copy; the rest is read from the CSR
 
 // Device-resident neighbour table of one z-slab.
@@ -135,6 +135,7 @@ struct ApplyParams {
     const uint2* sell;                    // interleaved copy of the table (thread-per-column kernel)
     const uint32_t* slice_base;
     int64_t slices_per_level;
+    uint32_t null_gate;                   // index of the all-masked record (= n_gates)
     int64_t ncol;                         // ny*nx
     int32_t nx, ny;
     int32_t z_begin;                      // global index of local level 0

@@ -79,3 +79,13 @@ def ulp_diff_f32(a, b):
     a = np.ascontiguousarray(a, dtype=np.float32).view(np.int32).astype(np.int64)
     b = np.ascontiguousarray(b, dtype=np.float32).view(np.int32).astype(np.int64)
     return np.abs(a - b)
+
+
+@pytest.fixture(autouse=True, scope="session")
+def _apply_variant_from_env():
+    """RG_APPLY_VARIANT_TEST=1 runs the gpu tests on the group-per-column kernel instead of the default one."""
+    v = os.environ.get("RG_APPLY_VARIANT_TEST")
+    if v and _has_device():
+        from radar_grid_b200 import _native as N
+        N.default_context().set_option("apply_variant", int(v))
+    yield

@@ -86,7 +86,7 @@ def main():
         open(dst, "w").write(text)
         cpps.append(dst)
     lib = os.path.join(OUT, "libradargrid_b200_emu.so")
-    cmd = ["g++", "-std=c++20", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-Wno-unknown-pragmas", *os.environ.get("RG_EMU_FLAGS", "").split(),
+    cmd = ["g++", "-std=c++20", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-Wno-unknown-pragmas", "-DRG_EMU", *os.environ.get("RG_EMU_FLAGS", "").split(),
            "-I", HERE, "-I", CSRC, "-I", os.path.join(ROOT, "include"), "-o", lib] + cpps
     res = subprocess.run(cmd, capture_output=True, text=True)
     sys.stderr.write(res.stderr[-6000:])
