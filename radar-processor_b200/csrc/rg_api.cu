@@ -230,6 +230,9 @@ int make_product_params(const rg_grid_spec& gs, int n_products, const rg_product
         }
     }
     pp->any = n_products > 0 ? 1 : 0;
+    pp->cmax_w = pp->cmax_on && pp->cmax_z1 >= pp->cmax_z0 ? (uint32_t)(pp->cmax_z1 - pp->cmax_z0 + 1) : 0u;
+    pp->cmin_w = pp->cmin_on && pp->cmin_z1 >= pp->cmin_z0 ? (uint32_t)(pp->cmin_z1 - pp->cmin_z0 + 1) : 0u;
+    pp->cmean_w = pp->cmean_on && pp->cmean_z1 >= pp->cmean_z0 ? (uint32_t)(pp->cmean_z1 - pp->cmean_z0 + 1) : 0u;
     int words = 0;
     pp->slot_cmax = pp->cmax_on ? words++ : -1;
     pp->slot_cmin = pp->cmin_on ? words++ : -1;

@@ -179,9 +179,10 @@ struct ColumnState {
     __device__ __forceinline__ void update(const ProductParams& pp, int z, float v)
     {
         const bool ok = !isnan(v);
-        if (pp.cmax_on && z >= pp.cmax_z0 && z <= pp.cmax_z1 && ok) cmax = isnan(cmax) ? v : fmaxf(cmax, v);
-        if (pp.cmin_on && z >= pp.cmin_z0 && z <= pp.cmin_z1 && ok) cmin = isnan(cmin) ? v : fminf(cmin, v);
-        if (pp.cmean_on && z >= pp.cmean_z0 && z <= pp.cmean_z1) {
+        // z0 <= z <= z1 as one unsigned compare against the range width (0 when the product is off)
+        if ((unsigned)(z - pp.cmax_z0) < pp.cmax_w && ok) cmax = isnan(cmax) ? v : fmaxf(cmax, v);
+        if ((unsigned)(z - pp.cmin_z0) < pp.cmin_w && ok) cmin = isnan(cmin) ? v : fminf(cmin, v);
+        if ((unsigned)(z - pp.cmean_z0) < pp.cmean_w) {
             // np.nanmean: NaN -> 0, sequential float32 adds along z, count of non-NaN
             msum = __fadd_rn(msum, ok ? v : 0.f);
             mcnt += ok ? 1 : 0;
@@ -522,9 +523,10 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
         e_next = __ldg(indptr + row + 1);
     }
 
+    size_t row = (size_t)p.lz_first * (size_t)p.ncol + (size_t)col - (size_t)p.ncol;
     for (int lz = p.lz_first; lz < p.lz_last; ++lz) {
         const uint32_t s = s_next, e = e_next;
-        const size_t row = (size_t)lz * (size_t)p.ncol + (size_t)col;
+        row += (size_t)p.ncol;
         if (col_ok && lz + 1 < p.lz_last) {                    // prefetch the next level's row bounds
             s_next = __ldg(indptr + row + (size_t)p.ncol);
             e_next = __ldg(indptr + row + (size_t)p.ncol + 1);

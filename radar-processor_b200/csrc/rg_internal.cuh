@@ -113,6 +113,7 @@ struct ProductParams {
     int32_t cmax_on, cmax_z0, cmax_z1;
     int32_t cmin_on, cmin_z0, cmin_z1;
     int32_t cmean_on, cmean_z0, cmean_z1;
+    uint32_t cmax_w, cmin_w, cmean_w;     // z1 - z0 + 1 when on, 0 when off
     int32_t n_slices;
     int32_t nz_full;
     float* cmax_out;
