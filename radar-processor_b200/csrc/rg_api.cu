@@ -859,6 +859,9 @@ int rg_apply(rg_context* c, const rg_geometry* geom, const rg_apply_args* a, int
     ap.slice_base = g->slice_base;
     ap.slices_per_level = g->slices_per_level;
     ap.null_gate = (uint32_t)G;
+    RG_TRY(bind_record_textures(ctx, pk.records, pk.records_b, F, G));
+    ap.tex_a = ctx->tex_a;
+    ap.tex_b = ctx->tex_b;
     ap.ncol = ncol;
     ap.nx = g->grid.nx;
     ap.ny = g->grid.ny;

@@ -78,12 +78,43 @@ __global__ void __launch_bounds__(256) pack_records_kernel(const __grid_constant
     if constexpr (FB > 0) store(p.records_b + (size_t)g * FB, out + FA, std::integral_constant<int, FB>{});
 }
 
+// (Re)create the texture objects over the record arrays when the buffer or the field count changed.
+int bind_record_textures(Context* ctx, const float* rec_a, const float* rec_b, int n_fields, int64_t n_gates)
+{
+#if RG_TEX && RG_VAR == 2 && !defined(RG_EMU)
+    if (ctx->tex_a_ptr == rec_a && ctx->tex_b_ptr == rec_b && ctx->tex_fields == n_fields) return RG_OK;
+    if (ctx->tex_a) { cudaDestroyTextureObject(ctx->tex_a); ctx->tex_a = 0; }
+    if (ctx->tex_b) { cudaDestroyTextureObject(ctx->tex_b); ctx->tex_b = 0; }
+    const int fa = n_fields == 1 ? 1 : n_fields == 2 ? 2 : 4;
+    const int fb = n_fields <= 4 ? 0 : n_fields == 5 ? 1 : n_fields == 6 ? 2 : 4;
+    auto make = [&](const float* ptr, int nf, unsigned long long* out) -> int {
+        cudaResourceDesc rd{};
+        rd.resType = cudaResourceTypeLinear;
+        rd.res.linear.devPtr = const_cast<float*>(ptr);
+        rd.res.linear.desc = cudaCreateChannelDesc(32, nf >= 2 ? 32 : 0, nf >= 4 ? 32 : 0, nf >= 4 ? 32 : 0, cudaChannelFormatKindFloat);
+        rd.res.linear.sizeInBytes = (size_t)(n_gates + 1) * nf * sizeof(float);
+        cudaTextureDesc td{};
+        td.readMode = cudaReadModeElementType;
+        cudaTextureObject_t t = 0;
+        RG_CUDA(cudaCreateTextureObject(&t, &rd, &td, nullptr));
+        *out = (unsigned long long)t;
+        return RG_OK;
+    };
+    RG_TRY(make(rec_a, fa, &ctx->tex_a));
+    if (fb > 0) RG_TRY(make(rec_b, fb, &ctx->tex_b));
+    ctx->tex_a_ptr = rec_a; ctx->tex_b_ptr = rec_b; ctx->tex_fields = n_fields;
+#else
+    (void)ctx; (void)rec_a; (void)rec_b; (void)n_fields; (void)n_gates;
+#endif
+    return RG_OK;
+}
+
 int records_width(int n_fields) { return n_fields <= 1 ? 1 : n_fields == 2 ? 2 : n_fields <= 4 ? 4 : 8; }
 
 size_t records_b_offset(int n_fields, int64_t n_gates)
 {
     const int fa = n_fields == 1 ? 1 : n_fields == 2 ? 2 : 4;
-    return (((size_t)(n_gates + 1) * fa * sizeof(float)) + 255) & ~(size_t)255;
+    return (((size_t)(n_gates + 1) * fa * sizeof(float)) + 511) & ~(size_t)511;   // texture-bindable
 }
 
 int launch_pack(Context* ctx, const PackParams& p)
@@ -214,6 +245,23 @@ struct ColumnState {
         }
     }
 
+    // the captured level pair of every slice is per column; kernels that keep no ColumnState in registers park it too
+    __device__ __forceinline__ void store_levels(const ProductParams& pp, float* sm, int n_fields) const
+    {
+        const int stride = blockDim.x;
+#pragma unroll
+        for (int k = 0; k < RG_MAX_SLICES; ++k)
+            if (pp.slot_slice[k] >= 0) sm[(pp.n_state_words * n_fields + k) * stride + threadIdx.x] = __int_as_float(zz[k]);
+    }
+
+    __device__ __forceinline__ void load_levels(const ProductParams& pp, const float* sm, int n_fields)
+    {
+        const int stride = blockDim.x;
+#pragma unroll
+        for (int k = 0; k < RG_MAX_SLICES; ++k)
+            zz[k] = pp.slot_slice[k] >= 0 ? __float_as_int(sm[(pp.n_state_words * n_fields + k) * stride + threadIdx.x]) : 0x7FFF7FFF;
+    }
+
     __device__ __forceinline__ void load_words(const ProductParams& pp, const float* sm, int f, int n_fields)
     {
         const int stride = blockDim.x, o = f * stride + threadIdx.x;
@@ -342,7 +390,10 @@ int launch_products(Context* ctx, const rg_grid_spec& grid, int n_fields, const 
 #define RG_UNROLL 4            // pairs (and their gathers) in flight per lane
 #endif
 #ifndef RG_MINBLOCKS
-#define RG_MINBLOCKS 1
+#define RG_MINBLOCKS 4
+#endif
+#ifndef RG_TEX
+#define RG_TEX 0               // 1: gather the gate records through the texture path (tex1Dfetch) instead of LDG
 #endif
 
 __device__ __forceinline__ void prefetch_l2(const void* ptr)
@@ -430,15 +481,33 @@ __device__ __forceinline__ void load_vec(const float* __restrict__ base, uint32_
     }
 }
 
-template <int F>
-__device__ __forceinline__ void load_record(const float* __restrict__ rec, const float* __restrict__ rec_b, uint32_t gate,
-                                            float (&v)[Layout<F>::NV])
+#if RG_TEX
+template <int N>
+__device__ __forceinline__ void tex_vec(cudaTextureObject_t t, uint32_t gate, float* v)
 {
-#if RG_VAR == 2
-    load_vec<Layout<F>::FA>(rec, gate, v);
-    if constexpr (Layout<F>::FB > 0) load_vec<Layout<F>::FB>(rec_b, gate, v + Layout<F>::FA);
+    if constexpr (N == 1) {
+        v[0] = tex1Dfetch<float>(t, (int)gate);
+    } else if constexpr (N == 2) {
+        const float2 q = tex1Dfetch<float2>(t, (int)gate);
+        v[0] = q.x; v[1] = q.y;
+    } else {
+        const float4 q = tex1Dfetch<float4>(t, (int)gate);
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    }
+}
+#endif
+
+template <int F>
+__device__ __forceinline__ void load_record(const RecSrc& r, uint32_t gate, float (&v)[Layout<F>::NV])
+{
+#if RG_TEX && RG_VAR == 2
+    tex_vec<Layout<F>::FA>(r.tex_a, gate, v);
+    if constexpr (Layout<F>::FB > 0) tex_vec<Layout<F>::FB>(r.tex_b, gate, v + Layout<F>::FA);
+#elif RG_VAR == 2
+    load_vec<Layout<F>::FA>(r.a, gate, v);
+    if constexpr (Layout<F>::FB > 0) load_vec<Layout<F>::FB>(r.b, gate, v + Layout<F>::FA);
 #else
-    load_vec<Layout<F>::FP>(rec, gate, v);
+    load_vec<Layout<F>::FP>(r.a, gate, v);
 #endif
 }
 
@@ -464,9 +533,8 @@ __device__ __forceinline__ void accumulate(float w, const float (&v)[NV], float 
 
 // Sum pairs [p, e) with stride `step`, RG_UNROLL pairs (and their gathers) in flight per lane.
 template <int F>
-__device__ __forceinline__ void gather_run(const uint2* __restrict__ pairs, const float* __restrict__ rec,
-                                           const float* __restrict__ rec_b, uint32_t p, uint32_t e, uint32_t step,
-                                           float (&swv)[F], float (&sw)[F])
+__device__ __forceinline__ void gather_run(const uint2* __restrict__ pairs, const RecSrc& rec, uint32_t p, uint32_t e,
+                                           uint32_t step, float (&swv)[F], float (&sw)[F])
 {
     constexpr int NV = Layout<F>::NV;
     constexpr int U = RG_UNROLL;
@@ -476,7 +544,7 @@ __device__ __forceinline__ void gather_run(const uint2* __restrict__ pairs, cons
         for (int j = 0; j < U; ++j) a[j] = __ldcs(pairs + p + j * step);
         float v[U][NV];
 #pragma unroll
-        for (int j = 0; j < U; ++j) load_record<F>(rec, rec_b, a[j].x, v[j]);
+        for (int j = 0; j < U; ++j) load_record<F>(rec, a[j].x, v[j]);
 #pragma unroll
         for (int j = 0; j < U; ++j) accumulate<F, NV>(__uint_as_float(a[j].y), v[j], swv, sw);
         p += U * step;
@@ -484,7 +552,7 @@ __device__ __forceinline__ void gather_run(const uint2* __restrict__ pairs, cons
     while (p < e) {
         const uint2 a0 = __ldcs(pairs + p);
         float v0[NV];
-        load_record<F>(rec, rec_b, a0.x, v0);
+        load_record<F>(rec, a0.x, v0);
         accumulate<F, NV>(__uint_as_float(a0.y), v0, swv, sw);
         p += step;
     }
@@ -503,17 +571,20 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
 
     const uint32_t* __restrict__ indptr = p.indptr;
     const uint2* __restrict__ pairs = p.pairs;
-    const float* __restrict__ rec = p.records;
-    const float* __restrict__ rec_b = p.records_b;
+    const RecSrc rec{p.records, p.records_b, p.tex_a, p.tex_b};
 
-    float x = 0.f, y = 0.f;
-    ColumnState st;
+    // per-lane product state (one field per owner lane) lives in shared memory: [word][thread]
+    extern __shared__ float sm_state[];
     if constexpr (PROD) {
+        float x = 0.f, y = 0.f;
         if (owner) {
             x = __ldg(p.prod.x_ax + (int)(col % p.nx));
             y = __ldg(p.prod.y_ax + (int)(col / p.nx));
         }
+        ColumnState st;
         st.init(p.prod, x, y);
+        st.store_words(p.prod, sm_state, 0, 1);
+        st.store_levels(p.prod, sm_state, 1);
     }
 
     uint32_t s_next = 0, e_next = 0;
@@ -560,7 +631,7 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
                 float hwv[F], hw[F];
 #pragma unroll
                 for (int f = 0; f < F; ++f) { hwv[f] = 0.f; hw[f] = 0.f; }
-                gather_run<F>(pairs, rec, rec_b, hs + lane, he, 32, hwv, hw);
+                gather_run<F>(pairs, rec, hs + lane, he, 32, hwv, hw);
 #pragma unroll
                 for (int f = 0; f < F; ++f) {
 #pragma unroll
@@ -578,7 +649,7 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
             heavy_mine = false;
         }
 
-        if (!heavy_mine) gather_run<F>(pairs, rec, rec_b, s + gl, e, W, swv, sw);
+        if (!heavy_mine) gather_run<F>(pairs, rec, s + gl, e, W, swv, sw);
 
         float a = 0.f, b = 0.f;
         if constexpr (RG_TREDUCE && W >= 8) {
@@ -611,12 +682,25 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
             const float v = b > 0.f ? __fdiv_rn(a, b) : p.fill;            // interpolate.py:99-102
             float* out = p.grid_out[gl];
             if (out != nullptr) __stcs(out + row, v);
-            if constexpr (PROD) st.update(p.prod, p.z_begin + lz, v);
+            if constexpr (PROD) {
+                ColumnState st;
+                st.load_words(p.prod, sm_state, 0, 1);
+                st.load_levels(p.prod, sm_state, 1);
+                st.update(p.prod, p.z_begin + lz, v);
+                st.store_words(p.prod, sm_state, 0, 1);
+            }
         }
     }
 
     if constexpr (PROD) {
-        if (owner) st.write(p.prod, gl, col, p.ncol, x, y);
+        if (owner) {
+            const float x = __ldg(p.prod.x_ax + (int)(col % p.nx));
+            const float y = __ldg(p.prod.y_ax + (int)(col / p.nx));
+            ColumnState st;
+            st.load_words(p.prod, sm_state, 0, 1);
+            st.load_levels(p.prod, sm_state, 1);
+            st.write(p.prod, gl, col, p.ncol, x, y);
+        }
     }
 }
 
@@ -646,8 +730,7 @@ __global__ void __launch_bounds__(kSellThreads) apply_sell_kernel(const __grid_c
 
     const uint32_t* __restrict__ indptr = p.indptr;
     const uint2* __restrict__ sell = p.sell;
-    const float* __restrict__ rec = p.records;
-    const float* __restrict__ rec_b = p.records_b;
+    const RecSrc rec{p.records, p.records_b, p.tex_a, p.tex_b};
 
     float x = 0.f, y = 0.f;
     ColumnState st;
@@ -708,7 +791,7 @@ __global__ void __launch_bounds__(kSellThreads) apply_sell_kernel(const __grid_c
             for (int j = 0; j < kDepth; ++j) pr[j] = act[j] ? __ldcs(sell + addr[j]) : make_uint2(p.null_gate, 0u);
             float v[kDepth][NV];
 #pragma unroll
-            for (int j = 0; j < kDepth; ++j) load_record<F>(rec, rec_b, pr[j].x, v[j]);
+            for (int j = 0; j < kDepth; ++j) load_record<F>(rec, pr[j].x, v[j]);
 #pragma unroll
             for (int j = 0; j < kDepth; ++j) accumulate<F, NV>(__uint_as_float(pr[j].y), v[j], swv, sw);
         }
@@ -723,7 +806,7 @@ __global__ void __launch_bounds__(kSellThreads) apply_sell_kernel(const __grid_c
             float hwv[F], hw[F];
 #pragma unroll
             for (int f = 0; f < F; ++f) { hwv[f] = 0.f; hw[f] = 0.f; }
-            gather_run<F>(p.pairs, rec, rec_b, hs + lane, he, 32, hwv, hw);
+            gather_run<F>(p.pairs, rec, hs + lane, he, 32, hwv, hw);
 #pragma unroll
             for (int f = 0; f < F; ++f) {
 #pragma unroll
@@ -1033,7 +1116,8 @@ static void launch_columns(Context* ctx, const ApplyParams& p)
 {
     const int cols_per_cta = kApplyThreads / W;
     const unsigned blocks = (unsigned)((p.ncol + cols_per_cta - 1) / cols_per_cta);
-    if (p.prod.any) apply_columns_kernel<F, W, true><<<blocks, kApplyThreads, 0, ctx->stream>>>(p);
+    const size_t smem = (size_t)(p.prod.n_state_words + RG_MAX_SLICES) * kApplyThreads * sizeof(float);
+    if (p.prod.any) apply_columns_kernel<F, W, true><<<blocks, kApplyThreads, smem, ctx->stream>>>(p);
     else apply_columns_kernel<F, W, false><<<blocks, kApplyThreads, 0, ctx->stream>>>(p);
 }
 

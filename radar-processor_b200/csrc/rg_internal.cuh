@@ -87,6 +87,10 @@ struct Context {
     int64_t sort_rows = 1;               // geometry build: order every row by gate id
     KernelTimer timers[kTimerCount];
     Scratch records;                     // packed gate records
+    unsigned long long tex_a = 0, tex_b = 0;   // texture objects over the record arrays (RG_TEX builds)
+    const void* tex_a_ptr = nullptr;
+    const void* tex_b_ptr = nullptr;
+    int tex_fields = 0;
     Scratch stage_in;                    // H2D staging of fields / masks / rule values
     Scratch stage_out;                   // device-side outputs of a host-memspace call
     Scratch misc;
@@ -137,6 +141,7 @@ struct ApplyParams {
     const uint32_t* slice_base;
     int64_t slices_per_level;
     uint32_t null_gate;                   // index of the all-masked record (= n_gates)
+    unsigned long long tex_a, tex_b;      // texture objects over records / records_b (RG_TEX builds)
     int64_t ncol;                         // ny*nx
     int32_t nx, ny;
     int32_t z_begin;                      // global index of local level 0
@@ -145,6 +150,12 @@ struct ApplyParams {
     float fill;
     float* grid_out[RG_MAX_FIELDS];
     ProductParams prod;
+};
+
+struct RecSrc {                           // where the apply kernels gather gate records from
+    const float* a;
+    const float* b;
+    unsigned long long tex_a, tex_b;
 };
 
 struct PackParams {
@@ -163,6 +174,7 @@ struct PackParams {
 };
 
 // ---- launchers (defined in the .cu files) -----------------------------------------------------------
+int bind_record_textures(Context* ctx, const float* rec_a, const float* rec_b, int n_fields, int64_t n_gates);
 int records_width(int n_fields);          // floats per packed gate record: 1, 2, 4 or 8
 size_t records_b_offset(int n_fields, int64_t n_gates);   // byte offset of array B inside the record buffer (RG_VAR 2)
 int launch_pack(Context* ctx, const PackParams& p);
