@@ -243,6 +243,15 @@ int make_product_params(const rg_grid_spec& gs, int n_products, const rg_product
         if (k < pp->n_slices) words += 2;
     }
     pp->n_state_words = words;
+    pp->n_ops = 0;
+    if (pp->cmax_w) pp->ops[pp->n_ops++] = {1, pp->cmax_z0, pp->cmax_z1, pp->slot_cmax, pp->cmax_w, 0};
+    if (pp->cmin_w) pp->ops[pp->n_ops++] = {2, pp->cmin_z0, pp->cmin_z1, pp->slot_cmin, pp->cmin_w, 0};
+    if (pp->cmean_w) pp->ops[pp->n_ops++] = {3, pp->cmean_z0, pp->cmean_z1, pp->slot_cmean, pp->cmean_w, 0};
+    for (int k = 0; k < pp->n_slices; ++k) {
+        const SliceParams& sl = pp->slices[k];
+        if (sl.kind == RG_PROD_BEAM) pp->ops[pp->n_ops++] = {5, 0, 0, pp->slot_slice[k], 0u, k};
+        else pp->ops[pp->n_ops++] = {4, sl.z_lo, sl.z_hi, pp->slot_slice[k], 0u, k};
+    }
     *z_need_lo = lo;
     *z_need_hi = hi;
     return RG_OK;

@@ -245,6 +245,43 @@ struct ColumnState {
         }
     }
 
+    // Update the shared-memory state of (field f, this thread) with the finished value v of GLOBAL level z.
+    // Same arithmetic as update(), driven by the op list so that only requested products cost anything.
+    static __device__ __forceinline__ void update_words(const ProductParams& pp, float* sm, int f, int n_fields, int z, float v)
+    {
+        const int stride = blockDim.x, o = f * stride + threadIdx.x;
+        const bool ok = !isnan(v);
+        for (int i = 0; i < pp.n_ops; ++i) {
+            const ProductParams::Op& op = pp.ops[i];
+            float* w0 = sm + op.slot * n_fields * stride + o;
+            switch (op.kind) {
+                case 1:
+                    if ((unsigned)(z - op.z0) < op.w && ok) { const float c = *w0; *w0 = isnan(c) ? v : fmaxf(c, v); }
+                    break;
+                case 2:
+                    if ((unsigned)(z - op.z0) < op.w && ok) { const float c = *w0; *w0 = isnan(c) ? v : fminf(c, v); }
+                    break;
+                case 3:
+                    if ((unsigned)(z - op.z0) < op.w) {
+                        float* w1 = w0 + n_fields * stride;
+                        *w0 = __fadd_rn(*w0, ok ? v : 0.f);
+                        *w1 = __int_as_float(__float_as_int(*w1) + (ok ? 1 : 0));
+                    }
+                    break;
+                case 4:                                   // warp-uniform levels: nothing to do on most levels
+                    if (z == op.z0) *w0 = v;
+                    if (z == op.z1) w0[n_fields * stride] = v;
+                    break;
+                default: {                                // per-column levels, parked next to the state words
+                    const int zz = __float_as_int(sm[(pp.n_state_words * n_fields + op.k) * stride + threadIdx.x]);
+                    if (z == (zz & 0xFFFF)) *w0 = v;
+                    if (z == (zz >> 16)) w0[n_fields * stride] = v;
+                    break;
+                }
+            }
+        }
+    }
+
     // the captured level pair of every slice is per column; kernels that keep no ColumnState in registers park it too
     __device__ __forceinline__ void store_levels(const ProductParams& pp, float* sm, int n_fields) const
     {
@@ -395,6 +432,23 @@ int launch_products(Context* ctx, const rg_grid_spec& grid, int n_fields, const 
 #ifndef RG_TEX
 #define RG_TEX 0               // 1: gather the gate records through the texture path (tex1Dfetch) instead of LDG
 #endif
+
+#ifndef RG_FASTDIV
+#define RG_FASTDIV 1           // fast path: a * rcp(b) refined once (<= 1 ulp off IEEE) instead of the IEEE division sequence
+#endif
+__device__ __forceinline__ float fast_div(float a, float b)
+{
+#if RG_FASTDIV && !defined(RG_EMU)
+    // b is a positive, finite sum of weights here; one Newton step on the hardware reciprocal
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+    r = fmaf(fmaf(-b, r, 1.0f), r, r);
+    const float q = a * r;
+    return fmaf(fmaf(-b, q, a), r, q);
+#else
+    return __fdiv_rn(a, b);
+#endif
+}
 
 __device__ __forceinline__ void prefetch_l2(const void* ptr)
 {
@@ -609,7 +663,8 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
             const size_t prow = row + (size_t)RG_PREFETCH * (size_t)p.ncol;
             const uint32_t ps = RG_PREFETCH == 1 ? s_next : __ldg(indptr + prow);
             const uint32_t pe = RG_PREFETCH == 1 ? e_next : __ldg(indptr + prow + 1);
-            for (uint32_t q = ps + 16u * gl; q < pe; q += 16u * W) prefetch_l2(pairs + q);
+            const uint32_t q = ps + 16u * gl;               // 16 pairs = one 128-byte line per lane
+            if (q < pe) prefetch_l2(pairs + q);
         }
 #endif
 
@@ -679,15 +734,11 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
         }
 
         if (owner) {
-            const float v = b > 0.f ? __fdiv_rn(a, b) : p.fill;            // interpolate.py:99-102
+            const float v = b > 0.f ? fast_div(a, b) : p.fill;             // interpolate.py:99-102
             float* out = p.grid_out[gl];
             if (out != nullptr) __stcs(out + row, v);
             if constexpr (PROD) {
-                ColumnState st;
-                st.load_words(p.prod, sm_state, 0, 1);
-                st.load_levels(p.prod, sm_state, 1);
-                st.update(p.prod, p.z_begin + lz, v);
-                st.store_words(p.prod, sm_state, 0, 1);
+                ColumnState::update_words(p.prod, sm_state, 0, 1, p.z_begin + lz, v);
             }
         }
     }
@@ -742,6 +793,7 @@ __global__ void __launch_bounds__(kSellThreads) apply_sell_kernel(const __grid_c
         st.init(p.prod, x, y);
 #pragma unroll
         for (int f = 0; f < F; ++f) st.store_words(p.prod, sm_state, f, F);
+        st.store_levels(p.prod, sm_state, F);
     }
 
     uint32_t s_next = 0, e_next = 0;
@@ -821,13 +873,11 @@ __global__ void __launch_bounds__(kSellThreads) apply_sell_kernel(const __grid_c
         if (col_ok) {
 #pragma unroll
             for (int f = 0; f < F; ++f) {
-                const float val = sw[f] > 0.f ? __fdiv_rn(swv[f], sw[f]) : p.fill;   // interpolate.py:99-102
+                const float val = sw[f] > 0.f ? fast_div(swv[f], sw[f]) : p.fill;    // interpolate.py:99-102
                 float* out = p.grid_out[f];
                 if (out != nullptr) __stcs(out + row, val);
                 if constexpr (PROD) {
-                    st.load_words(p.prod, sm_state, f, F);
-                    st.update(p.prod, p.z_begin + lz, val);
-                    st.store_words(p.prod, sm_state, f, F);
+                    ColumnState::update_words(p.prod, sm_state, f, F, p.z_begin + lz, val);
                 }
             }
         }
@@ -1145,7 +1195,7 @@ template <int F>
 static int launch_sell(Context* ctx, const ApplyParams& p)
 {
     const unsigned blocks = (unsigned)((p.ncol + kSellThreads - 1) / kSellThreads);
-    const size_t smem = p.prod.any ? (size_t)p.prod.n_state_words * F * kSellThreads * sizeof(float) : 0;
+    const size_t smem = p.prod.any ? (size_t)(p.prod.n_state_words * F + RG_MAX_SLICES) * kSellThreads * sizeof(float) : 0;
     if (p.prod.any) {
         if (smem > 48 * 1024)
             RG_CUDA(cudaFuncSetAttribute(apply_sell_kernel<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -127,7 +127,12 @@ struct ProductParams {
     const float* x_ax;
     const float* y_ax;
     SliceParams slices[RG_MAX_SLICES];
-    // shared-memory slots of the per-(field, column) product state in the thread-per-column kernel (-1 = unused)
+    // The same products as a short op list for kernels that keep the per-(field, column) state in shared memory:
+    // only requested products cost instructions.  kind 1 max, 2 min, 3 mean, 4 capture (uniform levels),
+    // 5 capture (per-column levels, BEAM).  slot = first state word.
+    int32_t n_ops;
+    struct Op { int32_t kind, z0, z1, slot; uint32_t w; int32_t k; } ops[3 + RG_MAX_SLICES];
+    // shared-memory slots of the per-(field, column) product state (-1 = unused)
     int32_t n_state_words;
     int32_t slot_cmax, slot_cmin, slot_cmean, slot_slice[RG_MAX_SLICES];
 };
