@@ -585,6 +585,10 @@ __device__ __forceinline__ void accumulate(float w, const float (&v)[NV], float 
     }
 }
 
+#ifndef RG_TAIL
+#define RG_TAIL 1              // 1: the tail of a row is ONE predicated batch (idle slots read the all-masked record)
+#endif
+
 // Sum pairs [p, e) with stride `step`, RG_UNROLL pairs (and their gathers) in flight per lane.
 template <int F>
 __device__ __forceinline__ void gather_run(const uint2* __restrict__ pairs, const RecSrc& rec, uint32_t p, uint32_t e,
@@ -603,6 +607,19 @@ __device__ __forceinline__ void gather_run(const uint2* __restrict__ pairs, cons
         for (int j = 0; j < U; ++j) accumulate<F, NV>(__uint_as_float(a[j].y), v[j], swv, sw);
         p += U * step;
     }
+#if RG_TAIL
+    if (p < e) {
+        // fewer than U pairs left for this lane: still one batch with all its loads in flight together
+        uint2 a[U - 1];
+#pragma unroll
+        for (int j = 0; j < U - 1; ++j) a[j] = p + j * step < e ? __ldcs(pairs + p + j * step) : make_uint2(rec.null_gate, 0u);
+        float v[U - 1][NV];
+#pragma unroll
+        for (int j = 0; j < U - 1; ++j) load_record<F>(rec, a[j].x, v[j]);
+#pragma unroll
+        for (int j = 0; j < U - 1; ++j) accumulate<F, NV>(__uint_as_float(a[j].y), v[j], swv, sw);
+    }
+#else
     while (p < e) {
         const uint2 a0 = __ldcs(pairs + p);
         float v0[NV];
@@ -610,11 +627,15 @@ __device__ __forceinline__ void gather_run(const uint2* __restrict__ pairs, cons
         accumulate<F, NV>(__uint_as_float(a0.y), v0, swv, sw);
         p += step;
     }
+#endif
 }
 
-template <int F, int W, bool PROD>
+// PSIG: 0 = no products, 1 = any product list (op list over shared-memory state), 2 = the operational request
+// "COLMAX and/or one level pick/blend (CAPPI)" with its three state words in registers.
+template <int F, int W, int PSIG>
 __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_kernel(const __grid_constant__ ApplyParams p)
 {
+    constexpr bool PROD = PSIG == 1;
     static_assert(W >= F || W == 32, "one lane per field in the epilogue");
     constexpr unsigned kFull = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
@@ -625,8 +646,10 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
 
     const uint32_t* __restrict__ indptr = p.indptr;
     const uint2* __restrict__ pairs = p.pairs;
-    const RecSrc rec{p.records, p.records_b, p.tex_a, p.tex_b};
+    const RecSrc rec{p.records, p.records_b, p.tex_a, p.tex_b, p.null_gate};
 
+    // PSIG 2: running max and the two captured levels in registers
+    float q_max = __uint_as_float(kCanonNaN), q_lo = q_max, q_hi = q_max;
     // per-lane product state (one field per owner lane) lives in shared memory: [word][thread]
     extern __shared__ float sm_state[];
     if constexpr (PROD) {
@@ -740,6 +763,21 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
             if constexpr (PROD) {
                 ColumnState::update_words(p.prod, sm_state, 0, 1, p.z_begin + lz, v);
             }
+            if constexpr (PSIG == 2) {
+                const int z = p.z_begin + lz;
+                if ((unsigned)(z - p.prod.cmax_z0) < p.prod.cmax_w && !isnan(v)) q_max = isnan(q_max) ? v : fmaxf(q_max, v);
+                if (z == p.prod.slices[0].z_lo) q_lo = v;
+                if (z == p.prod.slices[0].z_hi) q_hi = v;
+            }
+        }
+    }
+    if constexpr (PSIG == 2) {
+        if (owner) {
+            ColumnState st;
+            st.cmax = q_max;
+            st.s_lo[0] = q_lo;
+            st.s_hi[0] = q_hi;
+            st.write(p.prod, gl, col, p.ncol, 0.f, 0.f);       // only cmax and the LEVEL slice are on: x, y unused
         }
     }
 
@@ -781,7 +819,7 @@ __global__ void __launch_bounds__(kSellThreads) apply_sell_kernel(const __grid_c
 
     const uint32_t* __restrict__ indptr = p.indptr;
     const uint2* __restrict__ sell = p.sell;
-    const RecSrc rec{p.records, p.records_b, p.tex_a, p.tex_b};
+    const RecSrc rec{p.records, p.records_b, p.tex_a, p.tex_b, p.null_gate};
 
     float x = 0.f, y = 0.f;
     ColumnState st;
@@ -1167,8 +1205,12 @@ static void launch_columns(Context* ctx, const ApplyParams& p)
     const int cols_per_cta = kApplyThreads / W;
     const unsigned blocks = (unsigned)((p.ncol + cols_per_cta - 1) / cols_per_cta);
     const size_t smem = (size_t)(p.prod.n_state_words + RG_MAX_SLICES) * kApplyThreads * sizeof(float);
-    if (p.prod.any) apply_columns_kernel<F, W, true><<<blocks, kApplyThreads, smem, ctx->stream>>>(p);
-    else apply_columns_kernel<F, W, false><<<blocks, kApplyThreads, 0, ctx->stream>>>(p);
+    const ProductParams& pp = p.prod;
+    const bool simple = pp.any && !pp.cmin_on && !pp.cmean_on && pp.n_slices <= 1 &&
+                        (pp.n_slices == 0 || pp.slices[0].kind == RG_PROD_LEVEL) && ctx->apply_variant != 3;
+    if (!pp.any) apply_columns_kernel<F, W, 0><<<blocks, kApplyThreads, 0, ctx->stream>>>(p);
+    else if (simple) apply_columns_kernel<F, W, 2><<<blocks, kApplyThreads, 0, ctx->stream>>>(p);
+    else apply_columns_kernel<F, W, 1><<<blocks, kApplyThreads, smem, ctx->stream>>>(p);
 }
 
 template <int F>
@@ -1234,7 +1276,7 @@ int launch_apply(Context* ctx, const Geometry* g, const ApplyParams& p, bool ref
         RG_CUDA(cudaGetLastError());
         return RG_OK;
     }
-    if (ctx->apply_variant != 1) {                      // default: thread-per-column over the interleaved copy
+    if (ctx->apply_variant == 2) {                      // thread-per-column over the interleaved copy (kept for A/B)
         timer_begin(ctx, kTimerApply);
         int st = RG_OK;
         switch (p.n_fields) {

@@ -161,6 +161,7 @@ struct RecSrc {                           // where the apply kernels gather gate
     const float* a;
     const float* b;
     unsigned long long tex_a, tex_b;
+    uint32_t null_gate;
 };
 
 struct PackParams {

@@ -83,7 +83,7 @@ def ulp_diff_f32(a, b):
 
 @pytest.fixture(autouse=True, scope="session")
 def _apply_variant_from_env():
-    """RG_APPLY_VARIANT_TEST=1 runs the gpu tests on the group-per-column kernel instead of the default one."""
+    """RG_APPLY_VARIANT_TEST=N runs the gpu tests on apply kernel variant N (see rg_context_set_option) instead of the default."""
     v = os.environ.get("RG_APPLY_VARIANT_TEST")
     if v and _has_device():
         from radar_grid_b200 import _native as N
