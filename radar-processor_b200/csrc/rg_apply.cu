@@ -585,6 +585,9 @@ __device__ __forceinline__ void accumulate(float w, const float (&v)[NV], float 
     }
 }
 
+#ifndef RG_TILE2D
+#define RG_TILE2D 1            // CTA = 8 x 4 patch of columns (1) or 32 consecutive columns (0)
+#endif
 #ifndef RG_TAIL
 #define RG_TAIL 1              // 1: the tail of a row is ONE predicated batch (idle slots read the all-masked record)
 #endif
@@ -640,8 +643,20 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
     constexpr unsigned kFull = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
     const int gl = threadIdx.x & (W - 1);                      // lane within the column group
+#if RG_TILE2D
+    // A CTA covers a TX x TY patch of columns instead of a 1-D run: the neighbour sets of its columns overlap in
+    // both directions, so more of its gate-record gathers hit L1.  Groups of one warp stay adjacent in x.
+    constexpr int kGroups = kApplyThreads / W, TX = kGroups >= 8 ? 8 : kGroups, TY = kGroups / TX;
+    const int tiles_x = (p.nx + TX - 1) / TX;
+    const int g_in_cta = threadIdx.x / W;
+    const int cx = (int)(blockIdx.x % tiles_x) * TX + (g_in_cta % TX);
+    const int cy = (int)(blockIdx.x / tiles_x) * TY + (g_in_cta / TX);
+    const bool col_ok = cx < p.nx && cy < p.ny;
+    const int64_t col = col_ok ? (int64_t)cy * p.nx + cx : 0;
+#else
     const int64_t col = (int64_t)blockIdx.x * (kApplyThreads / W) + threadIdx.x / W;
     const bool col_ok = col < p.ncol;
+#endif
     const bool owner = col_ok && gl < F;                       // lane gl finishes field gl
 
     const uint32_t* __restrict__ indptr = p.indptr;
@@ -700,7 +715,7 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
         if constexpr (W < 32) {
             // Rows far longer than the group is wide (the voxels next to the radar see the first gates
             // of every ray) are summed by the whole warp, then handed back to the owning group.
-            unsigned heavy = __ballot_sync(kFull, heavy_mine && gl == 0);
+            unsigned heavy = __any_sync(kFull, heavy_mine) ? __ballot_sync(kFull, heavy_mine && gl == 0) : 0u;
             while (heavy) {
                 const int src = __ffs(heavy) - 1;
                 heavy &= heavy - 1;
@@ -1203,7 +1218,12 @@ template <int F, int W>
 static void launch_columns(Context* ctx, const ApplyParams& p)
 {
     const int cols_per_cta = kApplyThreads / W;
+#if RG_TILE2D
+    const int TX = cols_per_cta >= 8 ? 8 : cols_per_cta, TY = cols_per_cta / TX;
+    const unsigned blocks = (unsigned)(((p.nx + TX - 1) / TX) * ((p.ny + TY - 1) / TY));
+#else
     const unsigned blocks = (unsigned)((p.ncol + cols_per_cta - 1) / cols_per_cta);
+#endif
     const size_t smem = (size_t)(p.prod.n_state_words + RG_MAX_SLICES) * kApplyThreads * sizeof(float);
     const ProductParams& pp = p.prod;
     const bool simple = pp.any && !pp.cmin_on && !pp.cmean_on && pp.n_slices <= 1 &&

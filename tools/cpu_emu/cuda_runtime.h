@@ -81,6 +81,7 @@ inline unsigned __ballot_sync(unsigned, bool pred)
     emu_self.warp->bar->arrive_and_wait();
     return m;
 }
+inline bool __any_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) != 0; }
 inline unsigned __reduce_max_sync(unsigned, unsigned v)
 {
     emu_self.warp->xchg[emu_self.lane] = v;
