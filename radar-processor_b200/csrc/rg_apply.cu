@@ -679,6 +679,7 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
         st.store_levels(p.prod, sm_state, 1);
     }
 
+    float* const out = owner ? p.grid_out[gl] : nullptr;
     uint32_t s_next = 0, e_next = 0;
     if (col_ok && p.lz_first < p.lz_last) {
         const size_t row = (size_t)p.lz_first * (size_t)p.ncol + (size_t)col;
@@ -706,11 +707,14 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
         }
 #endif
 
+        const uint32_t len = e - s;
+        float a = 0.f, b = 0.f;
+        // warps whose four rows are all empty (outside the radar range, above the highest sweep) skip the sums
+        if (__any_sync(kFull, len != 0)) {
         float swv[F], sw[F];
 #pragma unroll
         for (int f = 0; f < F; ++f) { swv[f] = 0.f; sw[f] = 0.f; }
 
-        const uint32_t len = e - s;
         bool heavy_mine = len > kHeavyRow;
         if constexpr (W < 32) {
             // Rows far longer than the group is wide (the voxels next to the radar see the first gates
@@ -744,7 +748,6 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
 
         if (!heavy_mine) gather_run<F>(pairs, rec, s + gl, e, W, swv, sw);
 
-        float a = 0.f, b = 0.f;
         if constexpr (RG_TREDUCE && W >= 8) {
             // plain butterfly down to 8 lanes, then reduce-scatter: lane f of the group gets field f
 #pragma unroll
@@ -770,10 +773,10 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
             for (int f = 0; f < F; ++f)
                 if (gl == f) { a = swv[f]; b = sw[f]; }
         }
+        }
 
         if (owner) {
             const float v = b > 0.f ? fast_div(a, b) : p.fill;             // interpolate.py:99-102
-            float* out = p.grid_out[gl];
             if (out != nullptr) __stcs(out + row, v);
             if constexpr (PROD) {
                 ColumnState::update_words(p.prod, sm_state, 0, 1, p.z_begin + lz, v);

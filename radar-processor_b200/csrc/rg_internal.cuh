@@ -40,7 +40,10 @@ constexpr uint32_t kMaskedBits = 0xFFFFFFFFu;
 constexpr uint32_t kCanonNaN = 0x7FC00000u;
 constexpr uint32_t kInvalidCell = 0xFFFFFFFFu;
 
-constexpr int kApplyThreads = 256;       // threads per CTA of the column-tile apply kernel
+#ifndef RG_APPLY_THREADS
+#define RG_APPLY_THREADS 256
+#endif
+constexpr int kApplyThreads = RG_APPLY_THREADS;   // threads per CTA of the column-tile apply kernel
 constexpr uint32_t kHeavyRow = 512;      // rows longer than this are reduced by the whole warp
 constexpr int kSellThreads = 64;         // threads per CTA of the thread-per-column apply kernel
 constexpr uint32_t kSellCap = 192;       // pairs of a row kept in the interleaved copy; the rest is read from the CSR
