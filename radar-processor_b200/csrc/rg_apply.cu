@@ -599,6 +599,7 @@ __device__ __forceinline__ void gather_run(const uint2* __restrict__ pairs, cons
 {
     constexpr int NV = Layout<F>::NV;
     constexpr int U = RG_UNROLL;
+    static_assert(U >= 2 && U <= 4, "tail batch sizes are written out for U <= 4");
     while (p < e && e - p > (U - 1) * step) {
         uint2 a[U];
 #pragma unroll
@@ -611,16 +612,26 @@ __device__ __forceinline__ void gather_run(const uint2* __restrict__ pairs, cons
         p += U * step;
     }
 #if RG_TAIL
-    if (p < e) {
-        // fewer than U pairs left for this lane: still one batch with all its loads in flight together
-        uint2 a[U - 1];
+    // Tail: fewer than U pairs left per lane.  Still ONE batch with all its loads in flight together, sized by
+    // the longest remainder in the warp (idle slots read the all-masked record).
+    const uint32_t rem = p < e ? (e - p + step - 1) / step : 0u;
+    const uint32_t rmax = __reduce_max_sync(0xFFFFFFFFu, rem);
+    auto tail = [&](auto n) {
+        constexpr int N = decltype(n)::value;
+        uint2 a[N];
 #pragma unroll
-        for (int j = 0; j < U - 1; ++j) a[j] = p + j * step < e ? __ldcs(pairs + p + j * step) : make_uint2(rec.null_gate, 0u);
-        float v[U - 1][NV];
+        for (int j = 0; j < N; ++j) a[j] = p + j * step < e ? __ldcs(pairs + p + j * step) : make_uint2(rec.null_gate, 0u);
+        float v[N][NV];
 #pragma unroll
-        for (int j = 0; j < U - 1; ++j) load_record<F>(rec, a[j].x, v[j]);
+        for (int j = 0; j < N; ++j) load_record<F>(rec, a[j].x, v[j]);
 #pragma unroll
-        for (int j = 0; j < U - 1; ++j) accumulate<F, NV>(__uint_as_float(a[j].y), v[j], swv, sw);
+        for (int j = 0; j < N; ++j) accumulate<F, NV>(__uint_as_float(a[j].y), v[j], swv, sw);
+    };
+    if (rmax == 1) tail(std::integral_constant<int, 1>{});
+    else if (rmax == 2) tail(std::integral_constant<int, 2>{});
+    else if (rmax >= 3) {
+        if constexpr (U > 3) tail(std::integral_constant<int, 3>{});
+        else tail(std::integral_constant<int, 2>{});
     }
 #else
     while (p < e) {
@@ -746,7 +757,8 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
             heavy_mine = false;
         }
 
-        if (!heavy_mine) gather_run<F>(pairs, rec, s + gl, e, W, swv, sw);
+        // every lane calls (the tail batch is sized with a warp-wide reduction); a heavy group has nothing left
+        gather_run<F>(pairs, rec, heavy_mine ? e : s + gl, e, W, swv, sw);
 
         if constexpr (RG_TREDUCE && W >= 8) {
             // plain butterfly down to 8 lanes, then reduce-scatter: lane f of the group gets field f
@@ -1277,7 +1289,7 @@ static int pick_group_width(const Context* ctx, const Geometry* g, int n_fields)
     if (W == 0) {
         const int64_t nonempty = g->info.n_rows - g->info.n_empty_rows;
         const double avg = nonempty > 0 ? (double)g->info.n_pairs / (double)nonempty : 0.0;
-        W = avg < 6.0 ? 4 : avg < 96.0 ? 8 : avg < 400.0 ? 16 : 32;
+        W = avg < 24.0 ? 4 : avg < 160.0 ? 8 : avg < 600.0 ? 16 : 32;     // measured: cfg1 (avg 16) W=4, cfg3 (avg 40) W=8
     }
     if (W != 4 && W != 8 && W != 16 && W != 32) W = 8;
     if (W < 8 && n_fields > 4) W = 8;
