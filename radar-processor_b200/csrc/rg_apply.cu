@@ -599,6 +599,7 @@ __device__ __forceinline__ void gather_run(const uint2* __restrict__ pairs, cons
 {
     constexpr int NV = Layout<F>::NV;
     constexpr int U = RG_UNROLL;
+    static_assert(U >= 2 && U <= 4, "tail batch sizes are written out for U <= 4");
     while (p < e && e - p > (U - 1) * step) {
         uint2 a[U];
 #pragma unroll
@@ -611,16 +612,26 @@ __device__ __forceinline__ void gather_run(const uint2* __restrict__ pairs, cons
         p += U * step;
     }
 #if RG_TAIL
-    if (p < e) {
-        // fewer than U pairs left for this lane: still one batch with all its loads in flight together
-        uint2 a[U - 1];
+    // Tail: fewer than U pairs left per lane.  Still ONE batch with all its loads in flight together, sized by
+    // the longest remainder in the warp (idle slots read the all-masked record).
+    const uint32_t rem = p < e ? (e - p + step - 1) / step : 0u;
+    const uint32_t rmax = __reduce_max_sync(0xFFFFFFFFu, rem);
+    auto tail = [&](auto n) {
+        constexpr int N = decltype(n)::value;
+        uint2 a[N];
 #pragma unroll
-        for (int j = 0; j < U - 1; ++j) a[j] = p + j * step < e ? __ldcs(pairs + p + j * step) : make_uint2(rec.null_gate, 0u);
-        float v[U - 1][NV];
+        for (int j = 0; j < N; ++j) a[j] = p + j * step < e ? __ldcs(pairs + p + j * step) : make_uint2(rec.null_gate, 0u);
+        float v[N][NV];
 #pragma unroll
-        for (int j = 0; j < U - 1; ++j) load_record<F>(rec, a[j].x, v[j]);
+        for (int j = 0; j < N; ++j) load_record<F>(rec, a[j].x, v[j]);
 #pragma unroll
-        for (int j = 0; j < U - 1; ++j) accumulate<F, NV>(__uint_as_float(a[j].y), v[j], swv, sw);
+        for (int j = 0; j < N; ++j) accumulate<F, NV>(__uint_as_float(a[j].y), v[j], swv, sw);
+    };
+    if (rmax == 1) tail(std::integral_constant<int, 1>{});
+    else if (rmax == 2) tail(std::integral_constant<int, 2>{});
+    else if (rmax >= 3) {
+        if constexpr (U > 3) tail(std::integral_constant<int, 3>{});
+        else tail(std::integral_constant<int, 2>{});
     }
 #else
     while (p < e) {
@@ -680,14 +691,8 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
     }
 
     float* const out = owner ? p.grid_out[gl] : nullptr;
-    constexpr int NV = Layout<F>::NV;
-    constexpr int U = RG_UNROLL;
-    // Software pipeline over the levels of the column.  While level z is being summed,
-    //   - the row bounds of level z+2 are loaded,
-    //   - the first U pairs per lane of level z+1 are already in flight into registers (`nb`),
-    //   - (optionally) the rest of row z+1 is pulled from HBM into L2,
-    // so that the dependent chain bounds -> pairs -> gate records of a row never starts cold.
-    const uint2 null_pair = make_uint2(p.null_gate, 0u);
+    // Row bounds run two levels ahead of the sums, so that the L2 prefetch of level z+1 (issued while level z is
+    // summed) never waits for the bounds load it depends on.
     auto bounds = [&](int lz, uint32_t& bs, uint32_t& be) {
         bs = be = 0;
         if (col_ok && lz < p.lz_last) {
@@ -696,30 +701,21 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
             be = __ldg(indptr + r + 1);
         }
     };
-    auto first_batch = [&](uint32_t bs, uint32_t be, uint2 (&dst)[U]) {
-#pragma unroll
-        for (int j = 0; j < U; ++j) {
-            const uint32_t q = bs + gl + j * W;
-            dst[j] = (q < be && (W == 32 || be - bs <= kHeavyRow)) ? __ldcs(pairs + q) : null_pair;
-        }
-    };
-    uint32_t s = 0, e = 0, s1 = 0, e1 = 0;
-    bounds(p.lz_first, s, e);
-    bounds(p.lz_first + 1, s1, e1);
-    uint2 cb[U];
-    first_batch(s, e, cb);
+    uint32_t s_next, e_next, s_next2, e_next2;
+    bounds(p.lz_first, s_next, e_next);
+    bounds(p.lz_first + 1, s_next2, e_next2);
 
     size_t row = (size_t)p.lz_first * (size_t)p.ncol + (size_t)col - (size_t)p.ncol;
     for (int lz = p.lz_first; lz < p.lz_last; ++lz) {
+        const uint32_t s = s_next, e = e_next;
         row += (size_t)p.ncol;
-        uint32_t s2, e2;
-        bounds(lz + 2, s2, e2);
-        uint2 nb[U];
-        first_batch(s1, e1, nb);
+        s_next = s_next2;
+        e_next = e_next2;
+        bounds(lz + 2, s_next2, e_next2);
 #if RG_PREFETCH > 0
-        {   // the part of row z+1 the register prefetch does not cover: HBM -> L2, one 128-byte line per lane
-            const uint32_t q = s1 + U * W + 16u * gl;
-            if (q < e1) prefetch_l2(pairs + q);
+        {   // pull the pair lines of level z+1 from HBM into L2: one 128-byte line (16 pairs) per lane of the group
+            const uint32_t q = s_next + 16u * gl;
+            if (q < e_next) prefetch_l2(pairs + q);
         }
 #endif
 
@@ -762,14 +758,8 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
             heavy_mine = false;
         }
 
-        {   // light rows: the first batch is already in registers (idle slots and heavy rows hold the null pair)
-            float v[U][NV];
-#pragma unroll
-            for (int j = 0; j < U; ++j) load_record<F>(rec, cb[j].x, v[j]);
-#pragma unroll
-            for (int j = 0; j < U; ++j) accumulate<F, NV>(__uint_as_float(cb[j].y), v[j], swv, sw);
-            if (!heavy_mine) gather_run<F>(pairs, rec, s + gl + U * W, e, W, swv, sw);
-        }
+        // every lane calls (the tail batch is sized with a warp-wide reduction); a heavy group has nothing left
+        gather_run<F>(pairs, rec, heavy_mine ? e : s + gl, e, W, swv, sw);
 
         if constexpr (RG_TREDUCE && W >= 8) {
             // plain butterfly down to 8 lanes, then reduce-scatter: lane f of the group gets field f
@@ -811,10 +801,6 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
                 if (z == p.prod.slices[0].z_hi) q_hi = v;
             }
         }
-        // advance the pipeline
-#pragma unroll
-        for (int j = 0; j < U; ++j) cb[j] = nb[j];
-        s = s1; e = e1; s1 = s2; e1 = e2;
     }
     if constexpr (PSIG == 2) {
         if (owner) {
