@@ -450,10 +450,17 @@ __device__ __forceinline__ float fast_div(float a, float b)
 #endif
 }
 
+#ifndef RG_PREFETCH_L1
+#define RG_PREFETCH_L1 0       // 1: prefetch the next level's pair lines all the way into L1 instead of L2
+#endif
 __device__ __forceinline__ void prefetch_l2(const void* ptr)
 {
 #ifndef RG_EMU
+#if RG_PREFETCH_L1
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
+#else
     asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+#endif
 #else
     (void)ptr;
 #endif
@@ -599,7 +606,6 @@ __device__ __forceinline__ void gather_run(const uint2* __restrict__ pairs, cons
 {
     constexpr int NV = Layout<F>::NV;
     constexpr int U = RG_UNROLL;
-    static_assert(U >= 2 && U <= 4, "tail batch sizes are written out for U <= 4");
     while (p < e && e - p > (U - 1) * step) {
         uint2 a[U];
 #pragma unroll
@@ -612,26 +618,17 @@ __device__ __forceinline__ void gather_run(const uint2* __restrict__ pairs, cons
         p += U * step;
     }
 #if RG_TAIL
-    // Tail: fewer than U pairs left per lane.  Still ONE batch with all its loads in flight together, sized by
-    // the longest remainder in the warp (idle slots read the all-masked record).
-    const uint32_t rem = p < e ? (e - p + step - 1) / step : 0u;
-    const uint32_t rmax = __reduce_max_sync(0xFFFFFFFFu, rem);
-    auto tail = [&](auto n) {
-        constexpr int N = decltype(n)::value;
-        uint2 a[N];
+    if (p < e) {
+        // fewer than U pairs left for this lane: still one batch with all its loads in flight together
+        // (idle slots read the all-masked record)
+        uint2 a[U - 1];
 #pragma unroll
-        for (int j = 0; j < N; ++j) a[j] = p + j * step < e ? __ldcs(pairs + p + j * step) : make_uint2(rec.null_gate, 0u);
-        float v[N][NV];
+        for (int j = 0; j < U - 1; ++j) a[j] = p + j * step < e ? __ldcs(pairs + p + j * step) : make_uint2(rec.null_gate, 0u);
+        float v[U - 1][NV];
 #pragma unroll
-        for (int j = 0; j < N; ++j) load_record<F>(rec, a[j].x, v[j]);
+        for (int j = 0; j < U - 1; ++j) load_record<F>(rec, a[j].x, v[j]);
 #pragma unroll
-        for (int j = 0; j < N; ++j) accumulate<F, NV>(__uint_as_float(a[j].y), v[j], swv, sw);
-    };
-    if (rmax == 1) tail(std::integral_constant<int, 1>{});
-    else if (rmax == 2) tail(std::integral_constant<int, 2>{});
-    else if (rmax >= 3) {
-        if constexpr (U > 3) tail(std::integral_constant<int, 3>{});
-        else tail(std::integral_constant<int, 2>{});
+        for (int j = 0; j < U - 1; ++j) accumulate<F, NV>(__uint_as_float(a[j].y), v[j], swv, sw);
     }
 #else
     while (p < e) {
@@ -758,8 +755,7 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
             heavy_mine = false;
         }
 
-        // every lane calls (the tail batch is sized with a warp-wide reduction); a heavy group has nothing left
-        gather_run<F>(pairs, rec, heavy_mine ? e : s + gl, e, W, swv, sw);
+        if (!heavy_mine) gather_run<F>(pairs, rec, s + gl, e, W, swv, sw);
 
         if constexpr (RG_TREDUCE && W >= 8) {
             // plain butterfly down to 8 lanes, then reduce-scatter: lane f of the group gets field f
