@@ -570,10 +570,7 @@ int rg_geometry_from_csr(rg_context* c, const rg_grid_spec* grid, const void* in
         if (st != RG_OK) return bail(st);
     }
     g->info.n_rows = n_rows; g->info.n_pairs = n_pairs; g->info.n_gates = n_gates; g->info.grid = *grid;
-    {
-        const int st = build_sell(ctx, g);
-        if (st != RG_OK) return bail(st);
-    }
+    g->info.device_bytes = (int64_t)(((size_t)n_rows + 1) * 4 + (size_t)n_pairs * 8);
     {
         const int st = finalize_geometry_stats(ctx, g);
         if (st != RG_OK) return bail(st);
@@ -864,6 +861,8 @@ int rg_apply(rg_context* c, const rg_geometry* geom, const rg_apply_args* a, int
     ap.pairs = g->pairs;
     ap.records = pk.records;
     ap.records_b = pk.records_b;
+    if (ctx->apply_variant == 2 && g->sell == nullptr)      // the interleaved copy is only built for the A/B kernel
+        RG_TRY(build_sell(ctx, const_cast<Geometry*>(g)));
     ap.sell = g->sell;
     ap.slice_base = g->slice_base;
     ap.slices_per_level = g->slices_per_level;

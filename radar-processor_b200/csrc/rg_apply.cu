@@ -37,7 +37,7 @@ namespace rg {
 template <int FA, int FB>
 __global__ void __launch_bounds__(256) pack_records_kernel(const __grid_constant__ PackParams p)
 {
-    // FB == 0: one AoS array of FA floats per gate.  FB > 0 (RG_VAR 2): fields 0..FA-1 in array A, FA.. in array B.
+    // FB == 0: one AoS array of FA floats per gate.  FB > 0: fields 0..FA-1 in array A, FA.. in array B.
     constexpr int NV = FA + FB;
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g > p.n_gates) return;
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) pack_records_kernel(const __grid_constant
 // (Re)create the texture objects over the record arrays when the buffer or the field count changed.
 int bind_record_textures(Context* ctx, const float* rec_a, const float* rec_b, int n_fields, int64_t n_gates)
 {
-#if RG_TEX && RG_VAR == 2 && !defined(RG_EMU)
+#if RG_TEX && !defined(RG_EMU)
     if (ctx->tex_a_ptr == rec_a && ctx->tex_b_ptr == rec_b && ctx->tex_fields == n_fields) return RG_OK;
     if (ctx->tex_a) { cudaDestroyTextureObject(ctx->tex_a); ctx->tex_a = 0; }
     if (ctx->tex_b) { cudaDestroyTextureObject(ctx->tex_b); ctx->tex_b = 0; }
@@ -121,7 +121,6 @@ int launch_pack(Context* ctx, const PackParams& p)
 {
     const unsigned blocks = (unsigned)((p.n_gates + 1 + 255) / 256);
     timer_begin(ctx, kTimerPack);
-#if RG_VAR == 2
     switch (p.n_fields) {
         case 1: pack_records_kernel<1, 0><<<blocks, 256, 0, ctx->stream>>>(p); break;
         case 2: pack_records_kernel<2, 0><<<blocks, 256, 0, ctx->stream>>>(p); break;
@@ -130,14 +129,6 @@ int launch_pack(Context* ctx, const PackParams& p)
         case 6: pack_records_kernel<4, 2><<<blocks, 256, 0, ctx->stream>>>(p); break;
         default: pack_records_kernel<4, 4><<<blocks, 256, 0, ctx->stream>>>(p); break;
     }
-#else
-    switch (records_width(p.n_fields)) {
-        case 1: pack_records_kernel<1, 0><<<blocks, 256, 0, ctx->stream>>>(p); break;
-        case 2: pack_records_kernel<2, 0><<<blocks, 256, 0, ctx->stream>>>(p); break;
-        case 4: pack_records_kernel<4, 0><<<blocks, 256, 0, ctx->stream>>>(p); break;
-        default: pack_records_kernel<8, 0><<<blocks, 256, 0, ctx->stream>>>(p); break;
-    }
-#endif
     timer_end(ctx, kTimerPack);
     ctx->launches++;
     RG_CUDA(cudaGetLastError());
@@ -409,13 +400,10 @@ int launch_products(Context* ctx, const rg_grid_spec& grid, int n_fields, const 
 // ------------------------------------------------------------------------------------------------------
 // K5  fast path: column-tile CSR gather, W lanes per column, products in the epilogue
 //
-// Gate-record layouts (RG_VAR, a build-time choice so that variants can be measured side by side):
-//   0  AoS  float[G][FP]            masked values zeroed with selects           (first version, kept for A/B)
-//   1  AoS  float[G][FP]            predicated accumulate
-//   2  split A = float[G][FA] (fields 0..3) + B = float[G][FB] (fields 4..7), predicated accumulate:
-//      20 B per gate instead of 32 for five fields, no padding work
-//   3  AoS 32 B, two lanes per record: lane h of a pair loads half h (16 B) of two consecutive pairs'
-//      records, so one load instruction touches each 128-byte line once instead of twice
+// Gate records are split in two arrays, A = float[G][FA] (fields 0..3) and B = float[G][FB] (fields 4..7):
+// 20 bytes per gate for five fields, every float is a real field, and eight consecutive gates fill exactly one
+// 128-byte line of A.  (An interleaved 32-byte record and a two-lanes-per-record scheme were measured and lost,
+// see DESIGN.md section 6.)  The build-time switches below exist so that each design decision can be re-measured.
 // ------------------------------------------------------------------------------------------------------
 #ifndef RG_PREFETCH
 #define RG_PREFETCH 1          // levels of look-ahead for the L2 prefetch of the pair stream (0 = off)
@@ -450,17 +438,10 @@ __device__ __forceinline__ float fast_div(float a, float b)
 #endif
 }
 
-#ifndef RG_PREFETCH_L1
-#define RG_PREFETCH_L1 0       // 1: prefetch the next level's pair lines all the way into L1 instead of L2
-#endif
 __device__ __forceinline__ void prefetch_l2(const void* ptr)
 {
 #ifndef RG_EMU
-#if RG_PREFETCH_L1
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
-#else
     asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
-#endif
 #else
     (void)ptr;
 #endif
@@ -515,11 +496,7 @@ struct Layout {
     static constexpr int FP = F == 1 ? 1 : F == 2 ? 2 : F <= 4 ? 4 : 8;
     static constexpr int FA = F == 1 ? 1 : F == 2 ? 2 : 4;
     static constexpr int FB = F <= 4 ? 0 : F == 5 ? 1 : F == 6 ? 2 : 4;
-#if RG_VAR == 2
-    static constexpr int NV = FA + FB;
-#else
-    static constexpr int NV = FP;
-#endif
+    static constexpr int NV = FA + FB;           // floats gathered per gate
 };
 
 template <int N>
@@ -561,14 +538,12 @@ __device__ __forceinline__ void tex_vec(cudaTextureObject_t t, uint32_t gate, fl
 template <int F>
 __device__ __forceinline__ void load_record(const RecSrc& r, uint32_t gate, float (&v)[Layout<F>::NV])
 {
-#if RG_TEX && RG_VAR == 2
+#if RG_TEX
     tex_vec<Layout<F>::FA>(r.tex_a, gate, v);
     if constexpr (Layout<F>::FB > 0) tex_vec<Layout<F>::FB>(r.tex_b, gate, v + Layout<F>::FA);
-#elif RG_VAR == 2
+#else
     load_vec<Layout<F>::FA>(r.a, gate, v);
     if constexpr (Layout<F>::FB > 0) load_vec<Layout<F>::FB>(r.b, gate, v + Layout<F>::FA);
-#else
-    load_vec<Layout<F>::FP>(r.a, gate, v);
 #endif
 }
 
@@ -578,17 +553,10 @@ __device__ __forceinline__ void accumulate(float w, const float (&v)[NV], float 
 #pragma unroll
     for (int f = 0; f < F; ++f) {
         const bool m = __float_as_uint(v[f]) == kMaskedBits;   // interpolate.py:78-79
-#if RG_VAR == 0
-        const float we = m ? 0.f : w;
-        const float vv = m ? 0.f : v[f];
-        sw[f] = __fadd_rn(sw[f], we);
-        swv[f] = fmaf(we, vv, swv[f]);
-#else
-        if (!m) {
+        if (!m) {                                              // predicated: ISETP + FADD + FFMA per field
             sw[f] = __fadd_rn(sw[f], w);
             swv[f] = fmaf(w, v[f], swv[f]);
         }
-#endif
     }
 }
 
@@ -720,68 +688,68 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
         float a = 0.f, b = 0.f;
         // warps whose four rows are all empty (outside the radar range, above the highest sweep) skip the sums
         if (__any_sync(kFull, len != 0)) {
-        float swv[F], sw[F];
+            float swv[F], sw[F];
 #pragma unroll
-        for (int f = 0; f < F; ++f) { swv[f] = 0.f; sw[f] = 0.f; }
+            for (int f = 0; f < F; ++f) { swv[f] = 0.f; sw[f] = 0.f; }
 
-        bool heavy_mine = len > kHeavyRow;
-        if constexpr (W < 32) {
-            // Rows far longer than the group is wide (the voxels next to the radar see the first gates
-            // of every ray) are summed by the whole warp, then handed back to the owning group.
-            unsigned heavy = __any_sync(kFull, heavy_mine) ? __ballot_sync(kFull, heavy_mine && gl == 0) : 0u;
-            while (heavy) {
-                const int src = __ffs(heavy) - 1;
-                heavy &= heavy - 1;
-                const uint32_t hs = __shfl_sync(kFull, s, src);
-                const uint32_t he = __shfl_sync(kFull, e, src);
-                float hwv[F], hw[F];
+            bool heavy_mine = len > kHeavyRow;
+            if constexpr (W < 32) {
+                // Rows far longer than the group is wide (the voxels next to the radar see the first gates
+                // of every ray) are summed by the whole warp, then handed back to the owning group.
+                unsigned heavy = __any_sync(kFull, heavy_mine) ? __ballot_sync(kFull, heavy_mine && gl == 0) : 0u;
+                while (heavy) {
+                    const int src = __ffs(heavy) - 1;
+                    heavy &= heavy - 1;
+                    const uint32_t hs = __shfl_sync(kFull, s, src);
+                    const uint32_t he = __shfl_sync(kFull, e, src);
+                    float hwv[F], hw[F];
 #pragma unroll
-                for (int f = 0; f < F; ++f) { hwv[f] = 0.f; hw[f] = 0.f; }
-                gather_run<F>(pairs, rec, hs + lane, he, 32, hwv, hw);
+                    for (int f = 0; f < F; ++f) { hwv[f] = 0.f; hw[f] = 0.f; }
+                    gather_run<F>(pairs, rec, hs + lane, he, 32, hwv, hw);
+#pragma unroll
+                    for (int f = 0; f < F; ++f) {
+#pragma unroll
+                        for (int off = 16; off >= 1; off >>= 1) {
+                            hwv[f] += __shfl_xor_sync(kFull, hwv[f], off);
+                            hw[f] += __shfl_xor_sync(kFull, hw[f], off);
+                        }
+                    }
+                    if (lane == src) {                              // group leader keeps the row total
+#pragma unroll
+                        for (int f = 0; f < F; ++f) { swv[f] = hwv[f]; sw[f] = hw[f]; }
+                    }
+                }
+            } else {
+                heavy_mine = false;
+            }
+
+            if (!heavy_mine) gather_run<F>(pairs, rec, s + gl, e, W, swv, sw);
+
+            if constexpr (RG_TREDUCE && W >= 8) {
+                // plain butterfly down to 8 lanes, then reduce-scatter: lane f of the group gets field f
 #pragma unroll
                 for (int f = 0; f < F; ++f) {
 #pragma unroll
-                    for (int off = 16; off >= 1; off >>= 1) {
-                        hwv[f] += __shfl_xor_sync(kFull, hwv[f], off);
-                        hw[f] += __shfl_xor_sync(kFull, hw[f], off);
+                    for (int off = W / 2; off >= 8; off >>= 1) {
+                        swv[f] += __shfl_xor_sync(kFull, swv[f], off);
+                        sw[f] += __shfl_xor_sync(kFull, sw[f], off);
                     }
                 }
-                if (lane == src) {                              // group leader keeps the row total
+                group8_reduce_scatter<F>(swv, sw, gl & 7, a, b);
+            } else {
+                // butterfly inside the group: afterwards every lane of the group holds the row sums
 #pragma unroll
-                    for (int f = 0; f < F; ++f) { swv[f] = hwv[f]; sw[f] = hw[f]; }
+                for (int f = 0; f < F; ++f) {
+#pragma unroll
+                    for (int off = W / 2; off >= 1; off >>= 1) {
+                        swv[f] += __shfl_xor_sync(kFull, swv[f], off);
+                        sw[f] += __shfl_xor_sync(kFull, sw[f], off);
+                    }
                 }
+#pragma unroll
+                for (int f = 0; f < F; ++f)
+                    if (gl == f) { a = swv[f]; b = sw[f]; }
             }
-        } else {
-            heavy_mine = false;
-        }
-
-        if (!heavy_mine) gather_run<F>(pairs, rec, s + gl, e, W, swv, sw);
-
-        if constexpr (RG_TREDUCE && W >= 8) {
-            // plain butterfly down to 8 lanes, then reduce-scatter: lane f of the group gets field f
-#pragma unroll
-            for (int f = 0; f < F; ++f) {
-#pragma unroll
-                for (int off = W / 2; off >= 8; off >>= 1) {
-                    swv[f] += __shfl_xor_sync(kFull, swv[f], off);
-                    sw[f] += __shfl_xor_sync(kFull, sw[f], off);
-                }
-            }
-            group8_reduce_scatter<F>(swv, sw, gl & 7, a, b);
-        } else {
-            // butterfly inside the group: afterwards every lane of the group holds the row sums
-#pragma unroll
-            for (int f = 0; f < F; ++f) {
-#pragma unroll
-                for (int off = W / 2; off >= 1; off >>= 1) {
-                    swv[f] += __shfl_xor_sync(kFull, swv[f], off);
-                    sw[f] += __shfl_xor_sync(kFull, sw[f], off);
-                }
-            }
-#pragma unroll
-            for (int f = 0; f < F; ++f)
-                if (gl == f) { a = swv[f]; b = sw[f]; }
-        }
         }
 
         if (owner) {
@@ -959,157 +927,6 @@ __global__ void __launch_bounds__(kSellThreads) apply_sell_kernel(const __grid_c
     }
 }
 
-#if RG_VAR == 3
-// Lane-paired variant (32-byte records, F >= 5, 8 lanes per column = 4 slots x 2 halves).
-// Slot q of a group handles two consecutive pairs per step; lane h of the slot loads half h (fields 4h..4h+3)
-// of both records.  The group's partial sums are then reduced AND scattered in one go: after two halving
-// exchanges lane (h, q) holds the row total of field 4h + 2(q&1) + (q>>1), which it finishes itself.
-__device__ __forceinline__ void acc_half(float w, const float4& r, float (&swv)[4], float (&sw)[4])
-{
-    const float v[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-    for (int f = 0; f < 4; ++f) {
-        if (__float_as_uint(v[f]) != kMaskedBits) {
-            sw[f] = __fadd_rn(sw[f], w);
-            swv[f] = fmaf(w, v[f], swv[f]);
-        }
-    }
-}
-
-__device__ __forceinline__ void paired_run(const uint2* __restrict__ pairs, const float* __restrict__ rec, uint32_t s,
-                                           uint32_t e, uint32_t slot, uint32_t nslots, int h, float (&swv)[4], float (&sw)[4])
-{
-    const float4* __restrict__ rec4 = reinterpret_cast<const float4*>(rec);
-    const float mb = __uint_as_float(kMaskedBits);
-    const float4 masked = make_float4(mb, mb, mb, mb);
-    const uint32_t stride = 2 * nslots;
-    uint32_t p0 = s + 2 * slot;
-    while (p0 < e && e - p0 > stride + 1) {                    // two full steps: pairs p0, p0+1, p0+stride, p0+stride+1
-        const uint2 a0 = __ldcs(pairs + p0);
-        const uint2 a1 = __ldcs(pairs + p0 + 1);
-        const uint2 a2 = __ldcs(pairs + p0 + stride);
-        const uint2 a3 = __ldcs(pairs + p0 + stride + 1);
-        const float4 r0 = __ldg(rec4 + 2 * (size_t)a0.x + h);
-        const float4 r1 = __ldg(rec4 + 2 * (size_t)a1.x + h);
-        const float4 r2 = __ldg(rec4 + 2 * (size_t)a2.x + h);
-        const float4 r3 = __ldg(rec4 + 2 * (size_t)a3.x + h);
-        acc_half(__uint_as_float(a0.y), r0, swv, sw);
-        acc_half(__uint_as_float(a1.y), r1, swv, sw);
-        acc_half(__uint_as_float(a2.y), r2, swv, sw);
-        acc_half(__uint_as_float(a3.y), r3, swv, sw);
-        p0 += 2 * stride;
-    }
-    while (p0 < e) {
-        const bool two = p0 + 1 < e;
-        const uint2 a0 = __ldcs(pairs + p0);
-        const uint2 a1 = two ? __ldcs(pairs + p0 + 1) : make_uint2(0u, 0u);
-        const float4 r0 = __ldg(rec4 + 2 * (size_t)a0.x + h);
-        const float4 r1 = two ? __ldg(rec4 + 2 * (size_t)a1.x + h) : masked;
-        acc_half(__uint_as_float(a0.y), r0, swv, sw);
-        acc_half(__uint_as_float(a1.y), r1, swv, sw);
-        p0 += stride;
-    }
-}
-
-template <int F, bool PROD>
-__global__ void __launch_bounds__(kApplyThreads) apply_columns_paired_kernel(const __grid_constant__ ApplyParams p)
-{
-    static_assert(F >= 5 && F <= 8, "paired layout is for 32-byte records");
-    constexpr unsigned kFull = 0xFFFFFFFFu;
-    constexpr int W = 8;
-    const int lane = threadIdx.x & 31;
-    const int gl = lane & 7;
-    const int h = gl & 1;                                      // record half
-    const int q = gl >> 1;                                     // slot in the group
-    const int fld = 4 * h + 2 * (q & 1) + (q >> 1);            // field this lane finishes
-    const int64_t col = (int64_t)blockIdx.x * (kApplyThreads / W) + threadIdx.x / W;
-    const bool col_ok = col < p.ncol;
-    const bool owner = col_ok && fld < F;
-
-    const uint32_t* __restrict__ indptr = p.indptr;
-    const uint2* __restrict__ pairs = p.pairs;
-    const float* __restrict__ rec = p.records;
-
-    float x = 0.f, y = 0.f;
-    ColumnState st;
-    if constexpr (PROD) {
-        if (owner) {
-            x = __ldg(p.prod.x_ax + (int)(col % p.nx));
-            y = __ldg(p.prod.y_ax + (int)(col / p.nx));
-        }
-        st.init(p.prod, x, y);
-    }
-
-    uint32_t s_next = 0, e_next = 0;
-    if (col_ok && p.lz_first < p.lz_last) {
-        const size_t row = (size_t)p.lz_first * (size_t)p.ncol + (size_t)col;
-        s_next = __ldg(indptr + row);
-        e_next = __ldg(indptr + row + 1);
-    }
-
-    for (int lz = p.lz_first; lz < p.lz_last; ++lz) {
-        const uint32_t s = s_next, e = e_next;
-        const size_t row = (size_t)lz * (size_t)p.ncol + (size_t)col;
-        if (col_ok && lz + 1 < p.lz_last) {
-            s_next = __ldg(indptr + row + (size_t)p.ncol);
-            e_next = __ldg(indptr + row + (size_t)p.ncol + 1);
-        }
-        float swv[4] = {0.f, 0.f, 0.f, 0.f}, sw[4] = {0.f, 0.f, 0.f, 0.f};
-        const uint32_t len = e - s;
-        const bool heavy_mine = len > kHeavyRow;
-        unsigned heavy = __ballot_sync(kFull, heavy_mine && gl == 0);
-        while (heavy) {
-            const int src = __ffs(heavy) - 1;
-            heavy &= heavy - 1;
-            const uint32_t hs = __shfl_sync(kFull, s, src);
-            const uint32_t he = __shfl_sync(kFull, e, src);
-            float hwv[4] = {0.f, 0.f, 0.f, 0.f}, hw[4] = {0.f, 0.f, 0.f, 0.f};
-            paired_run(pairs, rec, hs, he, (uint32_t)(lane >> 1), 16u, h, hwv, hw);
-#pragma unroll
-            for (int f = 0; f < 4; ++f) {
-#pragma unroll
-                for (int off = 16; off >= 2; off >>= 1) {      // over the 16 slots, halves stay apart
-                    hwv[f] += __shfl_xor_sync(kFull, hwv[f], off);
-                    hw[f] += __shfl_xor_sync(kFull, hw[f], off);
-                }
-            }
-            if ((lane & ~1) == src) {                          // slot 0 of the owning group keeps the total
-#pragma unroll
-                for (int f = 0; f < 4; ++f) { swv[f] = hwv[f]; sw[f] = hw[f]; }
-            }
-        }
-        if (!heavy_mine) paired_run(pairs, rec, s, e, (uint32_t)q, 4u, h, swv, sw);
-
-        // reduce-scatter over the 4 slots: 6 shuffles instead of 16
-        float n_wv[2], n_w[2];
-        {
-            const bool up = q & 1;
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const float send_wv = up ? swv[j] : swv[j + 2];
-                const float send_w = up ? sw[j] : sw[j + 2];
-                const float keep_wv = up ? swv[j + 2] : swv[j];
-                const float keep_w = up ? sw[j + 2] : sw[j];
-                n_wv[j] = keep_wv + __shfl_xor_sync(kFull, send_wv, 2);
-                n_w[j] = keep_w + __shfl_xor_sync(kFull, send_w, 2);
-            }
-        }
-        const bool up2 = q >> 1;
-        const float a = (up2 ? n_wv[1] : n_wv[0]) + __shfl_xor_sync(kFull, up2 ? n_wv[0] : n_wv[1], 4);
-        const float b = (up2 ? n_w[1] : n_w[0]) + __shfl_xor_sync(kFull, up2 ? n_w[0] : n_w[1], 4);
-
-        if (owner) {
-            const float v = b > 0.f ? __fdiv_rn(a, b) : p.fill;
-            float* out = p.grid_out[fld];
-            if (out != nullptr) __stcs(out + row, v);
-            if constexpr (PROD) st.update(p.prod, p.z_begin + lz, v);
-        }
-    }
-    if constexpr (PROD) {
-        if (owner) st.write(p.prod, fld, col, p.ncol, x, y);
-    }
-}
-#endif  // RG_VAR == 3
 
 // ------------------------------------------------------------------------------------------------------
 // K5  reference-order path: reproduces np.add.reduceat's summation order, so that on the reference's own
@@ -1205,13 +1022,9 @@ __global__ void __launch_bounds__(128) apply_reference_order_kernel(const __grid
         if (out == nullptr) continue;
         float v = p.fill;
         if (e > s) {
-#if RG_VAR == 2
             const int fa = p.n_fields == 1 ? 1 : p.n_fields == 2 ? 2 : 4;
             const int fb = p.n_fields <= 4 ? 0 : p.n_fields == 5 ? 1 : p.n_fields == 6 ? 2 : 4;
             RowTerms<FP> t{p.pairs, f < fa ? p.records : p.records_b, f, false, f < fa ? fa : fb, f < fa ? f : f - fa};
-#else
-            RowTerms<FP> t{p.pairs, p.records, f, false, FP, f};
-#endif
             float swv = t.at(s);
             if (e - s > 1) swv = __fadd_rn(swv, pairwise_sum<FP>(t, s + 1, e - s - 1));
             t.weights_only = true;
@@ -1248,14 +1061,6 @@ static void launch_columns(Context* ctx, const ApplyParams& p)
 template <int F>
 static int launch_columns_w(Context* ctx, const ApplyParams& p, int W)
 {
-#if RG_VAR == 3
-    if constexpr (F >= 5) {
-        const unsigned blocks = (unsigned)((p.ncol + 31) / 32);
-        if (p.prod.any) apply_columns_paired_kernel<F, true><<<blocks, kApplyThreads, 0, ctx->stream>>>(p);
-        else apply_columns_paired_kernel<F, false><<<blocks, kApplyThreads, 0, ctx->stream>>>(p);
-        return RG_OK;
-    }
-#endif
     if constexpr (F <= 4) {
         if (W == 4) { launch_columns<F, 4>(ctx, p); return RG_OK; }
     }

@@ -710,7 +710,6 @@ int build_geometry_device(Context* ctx, const float* gx, const float* gy, const 
         RG_CUDA(cudaGetLastError());
     }
     out->n_rows = n_rows; out->n_pairs = (int64_t)n_pairs; out->ncol = ncol; out->n_levels = n_levels;
-    RG_TRY(build_sell(ctx, out));
     RG_CUDA(cudaEventRecord(ev1, ctx->stream));
     RG_CUDA(cudaStreamSynchronize(ctx->stream));
     float ms = 0.f;
@@ -724,6 +723,7 @@ int build_geometry_device(Context* ctx, const float* gx, const float* gy, const 
     out->info.n_rows = n_rows; out->info.n_pairs = (int64_t)n_pairs; out->info.n_gates = n_gates;
     out->info.n_gates_binned = (int64_t)n_binned; out->info.n_candidates = (int64_t)cand;
     out->info.build_ms = ms; out->info.cell_size = cell; out->info.grid = gs;
+    out->info.device_bytes = (int64_t)(((size_t)n_rows + 1) * 4 + (size_t)n_pairs * 8);
     return finalize_geometry_stats(ctx, out);
 }
 

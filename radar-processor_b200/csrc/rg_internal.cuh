@@ -8,10 +8,6 @@
 
 #include "radar_grid_b200.h"
 
-#ifndef RG_VAR
-#define RG_VAR 2          // gate-record layout / accumulate variant of the apply kernel, see rg_apply.cu
-#endif
-
 namespace rg {
 
 // ---- error plumbing ---------------------------------------------------------------------------------
@@ -143,8 +139,8 @@ struct ProductParams {
 struct ApplyParams {
     const uint32_t* indptr;
     const uint2* pairs;
-    const float* records;                 // [n_gates][FP]  (RG_VAR 2: fields 0..3)
-    const float* records_b;               // RG_VAR 2: fields 4..7
+    const float* records;                 // [n_gates + 1][FA]  fields 0..3 (last record: all masked)
+    const float* records_b;               // [n_gates + 1][FB]  fields 4..7
     const uint2* sell;                    // interleaved copy of the table (thread-per-column kernel)
     const uint32_t* slice_base;
     int64_t slices_per_level;
@@ -185,7 +181,7 @@ struct PackParams {
 // ---- launchers (defined in the .cu files) -----------------------------------------------------------
 int bind_record_textures(Context* ctx, const float* rec_a, const float* rec_b, int n_fields, int64_t n_gates);
 int records_width(int n_fields);          // floats per packed gate record: 1, 2, 4 or 8
-size_t records_b_offset(int n_fields, int64_t n_gates);   // byte offset of array B inside the record buffer (RG_VAR 2)
+size_t records_b_offset(int n_fields, int64_t n_gates);   // byte offset of array B inside the record buffer 
 int launch_pack(Context* ctx, const PackParams& p);
 int launch_apply(Context* ctx, const Geometry* g, const ApplyParams& p, bool reference_order);
 int launch_products(Context* ctx, const rg_grid_spec& grid, int n_fields, const float* const* grids_dev,

@@ -202,3 +202,90 @@ def test_linearity_and_constant_field_properties():
     np.testing.assert_array_equal(defined, np.diff(g["indptr"]).reshape(spec.grid_shape) > 0)
     np.testing.assert_allclose(res[3][defined], 7.25, rtol=1e-6)
     np.testing.assert_allclose(res[2][defined], (2 * res[0] + 3 * res[1])[defined], rtol=1e-4, atol=1e-4)
+
+
+def test_zslab_shards_concatenate_and_colmax_reduces():
+    """z-slab sharding: slabs built and gridded independently give the same rows bit for bit, and the
+    nan-aware max of the partial COLMAX planes is the COLMAX of the whole grid."""
+    import torch
+    from radar_grid_b200 import distributed as D
+    spec, radar, gates, fields, g = golden_case("small")
+    names = list(fields)
+    data = [np.ma.getdata(fields[n]) for n in names]
+    masks = [np.ma.getmaskarray(fields[n]) for n in names]
+    full = rg.grid_fields(build(spec, gates, "barnes2", 0), data, masks=masks, products=[rg.ColumnMax(), rg.ColumnMin()])
+    parts, cmax, cmin = [], None, None
+    for z0, z1 in D.zslab_ranges(spec.grid_shape[0], 3):
+        slab = build(spec, gates, "barnes2", 0, z_range=(z0, z1))
+        r = rg.grid_fields(slab, data, masks=masks, products=[rg.ColumnMax(), rg.ColumnMin()])
+        assert r["grids"][0].shape == (z1 - z0, spec.grid_shape[1], spec.grid_shape[2])
+        parts.append(r["grids"])
+        pm, pn = torch.from_numpy(r["products"][0].copy()), torch.from_numpy(r["products"][1].copy())
+        # what all_reduce(MAX/MIN) does across ranks, with the -inf/+inf encoding of "no data"
+        enc = lambda t, s: torch.where(torch.isnan(t), torch.full_like(t, s), t)
+        cmax = enc(pm, -np.inf) if cmax is None else torch.maximum(cmax, enc(pm, -np.inf))
+        cmin = enc(pn, np.inf) if cmin is None else torch.minimum(cmin, enc(pn, np.inf))
+    for f in range(len(names)):
+        assert_same(np.concatenate([p[f] for p in parts], axis=0), full["grids"][f], f"slab concat field {f}")
+    dec = lambda t, s: torch.where(t == s, torch.full_like(t, float("nan")), t).numpy()
+    assert_same(dec(cmax, -np.inf), full["products"][0], "z-slab COLMAX")
+    assert_same(dec(cmin, np.inf), full["products"][1], "z-slab COLMIN")
+    one = D.allreduce_nanmax(torch.from_numpy(full["products"][0].copy()))      # world size 1: identity incl. NaNs
+    assert_same(one.numpy(), full["products"][0])
+
+
+def test_device_buffers_match_host_buffers():
+    """torch CUDA tensors in / out (zero-copy, RG_DEVICE) give bit-identical results to NumPy buffers (RG_HOST)."""
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("torch sees no CUDA device")
+    spec, radar, gates, fields, g = golden_case("small")
+    dev = build(spec, gates, "barnes2", 0)
+    names = list(fields)
+    raw = [np.ma.getdata(fields[n]).copy() for n in names]
+    for n, r in zip(names, raw):
+        r[np.ma.getmaskarray(fields[n])] = np.nan
+    reqs = [rg.ColumnMax(), rg.CAPPI(1234.5), rg.PPI(2.3)]
+    host = rg.grid_fields(dev, raw, mask_invalid=True, products=reqs)
+    dten = [torch.from_numpy(r).cuda() for r in raw]
+    torch.cuda.synchronize()
+    devr = rg.grid_fields(dev, dten, mask_invalid=True, products=reqs)
+    dev.ctx.synchronize()
+    for a, b in zip(host["grids"], devr["grids"]):
+        assert b.is_cuda and b.dtype == torch.float32
+        assert_same(a, b.cpu().numpy())
+    for a, b in zip(host["products"], devr["products"]):
+        assert_same(a, b.cpu().numpy())
+
+
+def test_errors_mirror_the_reference():
+    spec, radar, gates, fields, g = golden_case("tiny")
+    with pytest.raises(ValueError):
+        rg.compute_grid_geometry(*gates, spec.grid_shape, spec.grid_limits, temp_dir="/nonexistent/dir")     # compute.py:173
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        with pytest.raises(ValueError):
+            rg.compute_grid_geometry(*gates, spec.grid_shape, spec.grid_limits, temp_dir=tmp, weighting="gauss")   # :176
+        geom = rg.compute_grid_geometry(*gates, spec.grid_shape, spec.grid_limits, temp_dir=tmp, min_radius=spec.min_radius,
+                                        beam_factor=spec.beam_factor, radar_altitude=0.0)
+    assert geom.radar_altitude == 0.0 and geom.n_pairs() == len(g["gate_indices"])
+    assert_same(geom.indptr.astype(np.int32), g["indptr"])
+    with pytest.raises(ValueError):
+        rg.apply_geometry(geom, fields["DBZH"], additional_filters="nope")                      # interpolate.py:56
+    grid = rg.apply_geometry(geom, fields["DBZH"])
+    with pytest.raises(ValueError):
+        rg.constant_altitude_ppi(grid, geom, 1000.0, interpolation="cubic")                     # products.py:415
+    with pytest.raises(ValueError):
+        rg.constant_elevation_ppi(grid, geom, 1.0, interpolation="cubic")                       # products.py:312
+    with pytest.raises(ValueError):
+        rg.column_max(grid, z_min_alt=1000.0)                                                  # products.py:467
+    bad = gates[0].copy()
+    bad[5] = np.nan
+    with pytest.raises(ValueError):
+        rg.DeviceGeometry.build(bad, gates[1], gates[2], spec.grid_shape, spec.grid_limits)     # cKDTree refuses non-finite data
+    # save / load round trip of a GPU-built geometry, then apply through the loaded (host CSR) twin
+    with tempfile.TemporaryDirectory() as tmp:
+        path = tmp + "/g.npz"
+        rg.save_geometry(geom, path)
+        again = rg.load_geometry(path)
+    assert_same(rg.apply_geometry(again, fields["DBZH"]), grid, "apply through a reloaded geometry")
