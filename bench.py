@@ -48,6 +48,16 @@ def load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the apply kernel from the committed ncu capture (per launch)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "apply_traffic.json")) as fh:
+            t = json.load(fh)
+        return float(t["traffic_bytes_per_launch"]) if t.get("workload") == workload else None
+    except Exception:
+        return None
+
+
 def algorithmic_bytes(P, V, G, F, ncol, grids=True, n_planes=2):
     """8P + 4(V+1) + 5FG + B_out, B_out = 4FV for the 3-D grids + 4F*ny*nx per 2-D product."""
     return 8 * P + 4 * (V + 1) + 5 * F * G + (4 * F * V if grids else 0) + n_planes * 4 * F * ncol
@@ -260,7 +270,7 @@ def run_b200(args):
             "device_vs_host_path_identical": bool(same),
         },
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": None,
+                     "frac": (achieved / peak) if achieved else None, "traffic": measured_traffic(spec.name),
                      "kernel": "apply_columns_kernel", "algorithmic_bytes": b_alg, "peak_source": peak_src,
                      "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None},
         "clocks": clocks,

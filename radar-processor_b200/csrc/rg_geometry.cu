@@ -593,7 +593,9 @@ int build_geometry_device(Context* ctx, const float* gx, const float* gy, const 
     double xlo, xhi, ylo, yhi, zlo, zhi;
     lohi(xa, 0, gs.nx, xlo, xhi);
     lohi(ya, 0, gs.ny, ylo, yhi);
-    lohi(za, gs.z_begin, gs.z_end, zlo, zhi);
+    // the cell grid is laid out for the WHOLE grid even when only a z-slab is built, so that every slab scans the
+    // gates in the same order and a slab's rows are bit-identical to the same rows of a full build
+    lohi(za, 0, gs.nz, zlo, zhi);
     const double ax = std::max(fabs(xlo), fabs(xhi)), ay = std::max(fabs(ylo), fabs(yhi)), az = std::max(fabs(zlo), fabs(zhi));
     const double rmax = std::max(min_radius, sqrt(ax * ax + ay * ay + az * az) * beam_factor);
     const double pad = rmax * (1.0 + 1e-6) + 1.0;
