@@ -285,8 +285,7 @@ def run_b200(args):
         line["cpu_baseline"] = cpu_baseline_from_table(dev, spec, fields_ma)
     if world > 1:
         dist.destroy_process_group()
-    if rank == 0:
-        print(json.dumps(line), flush=True)
+    return line if rank == 0 else None
 
 
 def cpu_baseline_from_table(dev, spec, fields_ma):
@@ -329,7 +328,7 @@ def _ref_apply(task):
 
 def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
-        return
+        return None
     import multiprocessing as mp
     from radar_grid_b200 import synthetic as S
     from oracle import radar_grid_oracle as O
@@ -389,7 +388,24 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    return line
+
+
+class _QuietStdout:
+    """Route stdout to stderr while the benchmark runs (NCCL and friends print banners to fd 1), so that the ONLY
+    thing on stdout is the final JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+        return False
 
 
 def main():
@@ -405,11 +421,15 @@ def main():
     if args.impl == "reference":
         args.steps = 3 if args.steps is None else max(1, args.steps)
         args.warmup = 1 if args.warmup is None else max(0, args.warmup)
-        run_reference(args)
+        with _QuietStdout():
+            line = run_reference(args)
     else:
         args.steps = 200 if args.steps is None else max(1, args.steps)
         args.warmup = 10 if args.warmup is None else max(3, args.warmup)
-        run_b200(args)
+        with _QuietStdout():
+            line = run_b200(args)
+    if line is not None:
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
