@@ -560,6 +560,9 @@ __device__ __forceinline__ void accumulate(float w, const float (&v)[NV], float 
     }
 }
 
+#ifndef RG_HEADBATCH
+#define RG_HEADBATCH 1         // 1: issue the pair loads of the first 2U-1 slots of a row together
+#endif
 #ifndef RG_TILE2D
 #define RG_TILE2D 1            // CTA = 8 x 4 patch of columns (1) or 32 consecutive columns (0)
 #endif
@@ -723,7 +726,34 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
                 heavy_mine = false;
             }
 
+#if RG_HEADBATCH
+            {
+                // Head of the row: the pair loads of the first 2U-1 slots of every lane are issued together, so
+                // that the second batch of gathers does not wait for another trip to L2 (most rows fit entirely).
+                constexpr int U = RG_UNROLL, H = 2 * U - 1, NV = Layout<F>::NV;
+                const uint32_t lim = heavy_mine ? s : e;               // heavy rows were summed by the whole warp
+                uint2 hp[H];
+#pragma unroll
+                for (int j = 0; j < H; ++j) hp[j] = s + gl + j * W < lim ? __ldcs(pairs + s + gl + j * W) : make_uint2(rec.null_gate, 0u);
+                {
+                    float v[U][NV];
+#pragma unroll
+                    for (int j = 0; j < U; ++j) load_record<F>(rec, hp[j].x, v[j]);
+#pragma unroll
+                    for (int j = 0; j < U; ++j) accumulate<F, NV>(__uint_as_float(hp[j].y), v[j], swv, sw);
+                }
+                if (__any_sync(kFull, s + gl + U * W < lim)) {
+                    float v[U - 1][NV];
+#pragma unroll
+                    for (int j = 0; j < U - 1; ++j) load_record<F>(rec, hp[U + j].x, v[j]);
+#pragma unroll
+                    for (int j = 0; j < U - 1; ++j) accumulate<F, NV>(__uint_as_float(hp[U + j].y), v[j], swv, sw);
+                }
+                if (__any_sync(kFull, s + gl + H * W < lim)) gather_run<F>(pairs, rec, min(s + gl + H * W, lim), lim, W, swv, sw);
+            }
+#else
             if (!heavy_mine) gather_run<F>(pairs, rec, s + gl, e, W, swv, sw);
+#endif
 
             if constexpr (RG_TREDUCE && W >= 8) {
                 // plain butterfly down to 8 lanes, then reduce-scatter: lane f of the group gets field f
