@@ -449,6 +449,53 @@ def grid_fields(geom: DeviceGeometry, fields: Sequence, masks: Optional[Sequence
     return {"grids": grids, "products": pouts, "_keep": (fheld, mheld, rheld)}
 
 
+class VolumePipeline:
+    """
+    Overlap the host<->device copies of consecutive volumes with the kernels of their neighbours.
+
+    ``grid_fields`` on host buffers is synchronous (H2D, pack, apply, D2H, wait).  A time series of volumes that
+    share one neighbour table (BASELINE config 4; reference examples/batch_processing.py does this with a
+    ThreadPoolExecutor around the CPU path) is instead fed through ``n_streams`` library contexts, each with its
+    own CUDA stream and staging buffers, driven by one Python thread each (the ctypes call releases the GIL):
+    while volume i runs its kernels, volume i+1 is on the H2D copy engine and volume i-1 on the D2H one.
+    Use pinned host arrays (``pinned_empty``) for inputs and outputs, otherwise the copies serialise.
+    """
+
+    def __init__(self, geom: DeviceGeometry, n_streams: int = 3):
+        from concurrent.futures import ThreadPoolExecutor
+        self.geom = geom
+        self.ctxs = [N.Context(geom.ctx.device) for _ in range(max(1, int(n_streams)))]
+        self._pool = ThreadPoolExecutor(len(self.ctxs))
+
+    def _run(self, slot, kwargs):
+        return grid_fields(self.geom, ctx=self.ctxs[slot], **kwargs)
+
+    def map(self, jobs: Sequence[dict]) -> List[Dict[str, object]]:
+        """Run ``grid_fields(geom, **job)`` for every job; job i uses context i % n_streams.  Results in order."""
+        n = len(self.ctxs)
+        lanes = [[] for _ in range(n)]
+        for i, job in enumerate(jobs):
+            lanes[i % n].append((i, job))
+
+        def work(slot):
+            return [(i, self._run(slot, job)) for i, job in lanes[slot]]
+
+        out: List[Optional[dict]] = [None] * len(jobs)
+        for fut in [self._pool.submit(work, s) for s in range(n)]:
+            for i, res in fut.result():
+                out[i] = res
+        return out
+
+    def kernel_launches(self) -> int:
+        return sum(c.kernel_launches() for c in self.ctxs)
+
+    def close(self):
+        self._pool.shutdown(wait=True)
+        for c in self.ctxs:
+            c.close()
+        self.ctxs = []
+
+
 def warn_all_nan(kind: str, plane: np.ndarray):
     """NumPy's nan-reductions warn when a column has no valid level; keep that observable behaviour."""
     if np.isnan(plane).any():
