@@ -310,6 +310,13 @@ def test_volume_pipeline_equals_sequential_calls():
                      "out_grids": [rg.pinned_empty((nz, ny, nx), np.float32) for _ in spec.fields]})
         expect.append(rg.grid_fields(dev, raw, mask_invalid=True, products=[rg.ColumnMax(), rg.CAPPI(4000.0)]))
     pipe = rg.VolumePipeline(dev, n_streams=3)
+    import os
+    if os.environ.get("RG_APPLY_VARIANT_TEST"):          # keep the A/B kernel selection consistent with `expect`
+        pipe.map(jobs[:1])                               # (the A/B kernel builds its table copy lazily: do it once, serially)
+        for c in pipe.ctxs:
+            c.set_option("apply_variant", int(os.environ["RG_APPLY_VARIANT_TEST"]))
+        pipe.ctxs[0].synchronize()
+        rg.grid_fields(dev, ctx=pipe.ctxs[0], **jobs[0])
     got = pipe.map(jobs)
     pipe.close()
     for e, r in zip(expect, got):
