@@ -538,9 +538,15 @@ __device__ __forceinline__ void tex_vec(cudaTextureObject_t t, uint32_t gate, fl
 template <int F>
 __device__ __forceinline__ void load_record(const RecSrc& r, uint32_t gate, float (&v)[Layout<F>::NV])
 {
-#if RG_TEX
+#if RG_TEX == 1
     tex_vec<Layout<F>::FA>(r.tex_a, gate, v);
     if constexpr (Layout<F>::FB > 0) tex_vec<Layout<F>::FB>(r.tex_b, gate, v + Layout<F>::FA);
+#elif RG_TEX == 2                                            // array A through LSU, the narrow array B through TEX
+    load_vec<Layout<F>::FA>(r.a, gate, v);
+    if constexpr (Layout<F>::FB > 0) tex_vec<Layout<F>::FB>(r.tex_b, gate, v + Layout<F>::FA);
+#elif RG_TEX == 3                                            // the other way round
+    tex_vec<Layout<F>::FA>(r.tex_a, gate, v);
+    if constexpr (Layout<F>::FB > 0) load_vec<Layout<F>::FB>(r.b, gate, v + Layout<F>::FA);
 #else
     load_vec<Layout<F>::FA>(r.a, gate, v);
     if constexpr (Layout<F>::FB > 0) load_vec<Layout<F>::FB>(r.b, gate, v + Layout<F>::FA);
