@@ -415,7 +415,7 @@ int launch_products(Context* ctx, const rg_grid_spec& grid, int n_fields, const 
 #define RG_UNROLL 4            // pairs (and their gathers) in flight per lane
 #endif
 #ifndef RG_MINBLOCKS
-#define RG_MINBLOCKS 4
+#define RG_MINBLOCKS (1024 / RG_APPLY_THREADS)     // 64 registers per thread: 32 resident warps per SM
 #endif
 #ifndef RG_TEX
 #define RG_TEX 0               // 1: gather the gate records through the texture path (tex1Dfetch) instead of LDG

@@ -37,7 +37,7 @@ constexpr uint32_t kCanonNaN = 0x7FC00000u;
 constexpr uint32_t kInvalidCell = 0xFFFFFFFFu;
 
 #ifndef RG_APPLY_THREADS
-#define RG_APPLY_THREADS 256
+#define RG_APPLY_THREADS 128
 #endif
 constexpr int kApplyThreads = RG_APPLY_THREADS;   // threads per CTA of the column-tile apply kernel
 constexpr uint32_t kHeavyRow = 512;      // rows longer than this are reduced by the whole warp
