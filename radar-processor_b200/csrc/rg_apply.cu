@@ -566,6 +566,9 @@ __device__ __forceinline__ void accumulate(float w, const float (&v)[NV], float 
     }
 }
 
+#ifndef RG_SMEMREDUCE
+#define RG_SMEMREDUCE 1        // 1: combine the lanes' row sums through shared memory, 0: shuffles (RG_TREDUCE)
+#endif
 #ifndef RG_HEADBATCH
 #define RG_HEADBATCH 1         // 1: issue the pair loads of the first 2U-1 slots of a row together
 #endif
@@ -648,6 +651,8 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
     const uint2* __restrict__ pairs = p.pairs;
     const RecSrc rec{p.records, p.records_b, p.tex_a, p.tex_b, p.null_gate};
 
+    constexpr int kRedStride = 36;                             // 32 lanes + 4: vector reads of one group hit distinct banks
+    __shared__ __align__(16) float red_buf[RG_SMEMREDUCE ? kApplyThreads / 32 : 1][RG_SMEMREDUCE ? 2 * F * kRedStride : 4];
     // PSIG 2: running max and the two captured levels in registers
     float q_max = __uint_as_float(kCanonNaN), q_lo = q_max, q_hi = q_max;
     // per-lane product state (one field per owner lane) lives in shared memory: [word][thread]
@@ -748,12 +753,21 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
 #pragma unroll
                     for (int j = 0; j < U; ++j) accumulate<F, NV>(__uint_as_float(hp[j].y), v[j], swv, sw);
                 }
+                // the rest of the head in two finer steps, each only if some lane of the warp still has pairs there
+                constexpr int H1 = U + (U - 1 + 1) / 2;                          // slots [U, H1) and [H1, H)
                 if (__any_sync(kFull, s + gl + U * W < lim)) {
-                    float v[U - 1][NV];
+                    float v[H1 - U][NV];
 #pragma unroll
-                    for (int j = 0; j < U - 1; ++j) load_record<F>(rec, hp[U + j].x, v[j]);
+                    for (int j = 0; j < H1 - U; ++j) load_record<F>(rec, hp[U + j].x, v[j]);
 #pragma unroll
-                    for (int j = 0; j < U - 1; ++j) accumulate<F, NV>(__uint_as_float(hp[U + j].y), v[j], swv, sw);
+                    for (int j = 0; j < H1 - U; ++j) accumulate<F, NV>(__uint_as_float(hp[U + j].y), v[j], swv, sw);
+                }
+                if (H > H1 && __any_sync(kFull, s + gl + H1 * W < lim)) {
+                    float v[H - H1 > 0 ? H - H1 : 1][NV];
+#pragma unroll
+                    for (int j = 0; j < H - H1; ++j) load_record<F>(rec, hp[H1 + j].x, v[j]);
+#pragma unroll
+                    for (int j = 0; j < H - H1; ++j) accumulate<F, NV>(__uint_as_float(hp[H1 + j].y), v[j], swv, sw);
                 }
                 if (__any_sync(kFull, s + gl + H * W < lim)) gather_run<F>(pairs, rec, min(s + gl + H * W, lim), lim, W, swv, sw);
             }
@@ -761,7 +775,31 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
             if (!heavy_mine) gather_run<F>(pairs, rec, s + gl, e, W, swv, sw);
 #endif
 
-            if constexpr (RG_TREDUCE && W >= 8) {
+            if constexpr (RG_SMEMREDUCE && W <= 16) {
+                // Transpose through shared memory: every lane parks its 2F partial sums (conflict-free rows of 32),
+                // then lane f of a group reads the W partials of field f with 128-bit loads and adds them up:
+                // 2F stores + W/2 vector loads + 2(W-1) adds instead of 14 shuffles with 2 selects and an add each.
+                float* red = red_buf[threadIdx.x >> 5];
+#pragma unroll
+                for (int f = 0; f < F; ++f) {
+                    red[f * kRedStride + lane] = swv[f];
+                    red[(F + f) * kRedStride + lane] = sw[f];
+                }
+                __syncwarp();
+                const int fo = gl < F ? gl : F - 1;                         // idle lanes read a valid row
+                const float4* pa = reinterpret_cast<const float4*>(red + fo * kRedStride + (lane & ~(W - 1)));
+                const float4* pb = reinterpret_cast<const float4*>(red + (F + fo) * kRedStride + (lane & ~(W - 1)));
+                float4 qa = pa[0], qb = pb[0];
+                a = (qa.x + qa.y) + (qa.z + qa.w);
+                b = (qb.x + qb.y) + (qb.z + qb.w);
+#pragma unroll
+                for (int k = 1; k < W / 4; ++k) {
+                    qa = pa[k]; qb = pb[k];
+                    a += (qa.x + qa.y) + (qa.z + qa.w);
+                    b += (qb.x + qb.y) + (qb.z + qb.w);
+                }
+                __syncwarp();
+            } else if constexpr (RG_TREDUCE && W >= 8) {
                 // plain butterfly down to 8 lanes, then reduce-scatter: lane f of the group gets field f
 #pragma unroll
                 for (int f = 0; f < F; ++f) {

@@ -23,6 +23,7 @@
 #define __launch_bounds__(...)
 #define __grid_constant__
 #define __shared__ static
+#define __align__(n) __attribute__((aligned(n)))
 
 struct uint2 { unsigned x, y; };
 struct float2 { float x, y; };
