@@ -438,6 +438,32 @@ __device__ __forceinline__ float fast_div(float a, float b)
 #endif
 }
 
+#ifndef RG_ASYNCHEAD
+#define RG_ASYNCHEAD 1         // 1: the head of the NEXT level's row is copied global->shared with cp.async while this level is summed
+#endif
+// 8-byte asynchronous copy global -> shared (LDGSTS): no destination register, completion tracked per thread
+__device__ __forceinline__ void cp_async8(uint2* smem_dst, const uint2* gmem_src)
+{
+#ifndef RG_EMU
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
+#else
+    *smem_dst = *gmem_src;
+#endif
+}
+__device__ __forceinline__ void cp_async_commit()
+{
+#ifndef RG_EMU
+    asm volatile("cp.async.commit_group;");
+#endif
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait()          // all but the N most recent groups of this thread have landed
+{
+#ifndef RG_EMU
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+
 __device__ __forceinline__ void prefetch_l2(const void* ptr)
 {
 #ifndef RG_EMU
@@ -566,9 +592,6 @@ __device__ __forceinline__ void accumulate(float w, const float (&v)[NV], float 
     }
 }
 
-#ifndef RG_SMEMREDUCE
-#define RG_SMEMREDUCE 1        // 1: combine the lanes' row sums through shared memory, 0: shuffles (RG_TREDUCE)
-#endif
 #ifndef RG_HEADBATCH
 #define RG_HEADBATCH 1         // 1: issue the pair loads of the first 2U-1 slots of a row together
 #endif
@@ -651,8 +674,6 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
     const uint2* __restrict__ pairs = p.pairs;
     const RecSrc rec{p.records, p.records_b, p.tex_a, p.tex_b, p.null_gate};
 
-    constexpr int kRedStride = 36;                             // 32 lanes + 4: vector reads of one group hit distinct banks
-    __shared__ __align__(16) float red_buf[RG_SMEMREDUCE ? kApplyThreads / 32 : 1][RG_SMEMREDUCE ? 2 * F * kRedStride : 4];
     // PSIG 2: running max and the two captured levels in registers
     float q_max = __uint_as_float(kCanonNaN), q_lo = q_max, q_hi = q_max;
     // per-lane product state (one field per owner lane) lives in shared memory: [word][thread]
@@ -683,6 +704,24 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
     uint32_t s_next, e_next, s_next2, e_next2;
     bounds(p.lz_first, s_next, e_next);
     bounds(p.lz_first + 1, s_next2, e_next2);
+#if RG_ASYNCHEAD && RG_HEADBATCH
+    // Head staging: while level z is summed, every lane copies the first 2U-1 pairs it will need at level z+1 from
+    // global to its own shared-memory slots with cp.async (no registers held, nobody else reads the slots), so
+    // the gathers of a row start from a shared-memory read instead of a trip to L2.  Double-buffered by level parity.
+    constexpr int kHead = 2 * RG_UNROLL - 1;
+    __shared__ uint2 head_sm[2][kHead][kApplyThreads];
+    auto stage_head = [&](int stage, uint32_t bs, uint32_t be) {
+        if (W < 32 && be - bs > kHeavyRow) return;             // heavy rows are read by the whole warp from global
+#pragma unroll
+        for (int j = 0; j < kHead; ++j) {
+            const uint32_t q = bs + gl + j * W;
+            if (q < be) cp_async8(&head_sm[stage][j][threadIdx.x], pairs + q);
+        }
+    };
+    stage_head(0, s_next, e_next);
+    cp_async_commit();
+    int stage = 0;
+#endif
 
     size_t row = (size_t)p.lz_first * (size_t)p.ncol + (size_t)col - (size_t)p.ncol;
     for (int lz = p.lz_first; lz < p.lz_last; ++lz) {
@@ -691,9 +730,17 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
         s_next = s_next2;
         e_next = e_next2;
         bounds(lz + 2, s_next2, e_next2);
+#if RG_ASYNCHEAD && RG_HEADBATCH
+        stage_head(stage ^ 1, s_next, e_next);                 // level z+1 (bounds arrived an iteration ago)
+        cp_async_commit();
+#endif
 #if RG_PREFETCH > 0
         {   // pull the pair lines of level z+1 from HBM into L2: one 128-byte line (16 pairs) per lane of the group
+#if RG_ASYNCHEAD && RG_HEADBATCH
+            const uint32_t q = s_next + kHead * W + 16u * gl;  // the part the head staging does not cover
+#else
             const uint32_t q = s_next + 16u * gl;
+#endif
             if (q < e_next) prefetch_l2(pairs + q);
         }
 #endif
@@ -744,8 +791,14 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
                 constexpr int U = RG_UNROLL, H = 2 * U - 1, NV = Layout<F>::NV;
                 const uint32_t lim = heavy_mine ? s : e;               // heavy rows were summed by the whole warp
                 uint2 hp[H];
+#if RG_ASYNCHEAD
+                cp_async_wait<1>();                                    // this level's head has landed; the next one may still fly
+#pragma unroll
+                for (int j = 0; j < H; ++j) hp[j] = s + gl + j * W < lim ? head_sm[stage][j][threadIdx.x] : make_uint2(rec.null_gate, 0u);
+#else
 #pragma unroll
                 for (int j = 0; j < H; ++j) hp[j] = s + gl + j * W < lim ? __ldcs(pairs + s + gl + j * W) : make_uint2(rec.null_gate, 0u);
+#endif
                 {
                     float v[U][NV];
 #pragma unroll
@@ -753,21 +806,12 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
 #pragma unroll
                     for (int j = 0; j < U; ++j) accumulate<F, NV>(__uint_as_float(hp[j].y), v[j], swv, sw);
                 }
-                // the rest of the head in two finer steps, each only if some lane of the warp still has pairs there
-                constexpr int H1 = U + (U - 1 + 1) / 2;                          // slots [U, H1) and [H1, H)
                 if (__any_sync(kFull, s + gl + U * W < lim)) {
-                    float v[H1 - U][NV];
+                    float v[U - 1][NV];
 #pragma unroll
-                    for (int j = 0; j < H1 - U; ++j) load_record<F>(rec, hp[U + j].x, v[j]);
+                    for (int j = 0; j < U - 1; ++j) load_record<F>(rec, hp[U + j].x, v[j]);
 #pragma unroll
-                    for (int j = 0; j < H1 - U; ++j) accumulate<F, NV>(__uint_as_float(hp[U + j].y), v[j], swv, sw);
-                }
-                if (H > H1 && __any_sync(kFull, s + gl + H1 * W < lim)) {
-                    float v[H - H1 > 0 ? H - H1 : 1][NV];
-#pragma unroll
-                    for (int j = 0; j < H - H1; ++j) load_record<F>(rec, hp[H1 + j].x, v[j]);
-#pragma unroll
-                    for (int j = 0; j < H - H1; ++j) accumulate<F, NV>(__uint_as_float(hp[H1 + j].y), v[j], swv, sw);
+                    for (int j = 0; j < U - 1; ++j) accumulate<F, NV>(__uint_as_float(hp[U + j].y), v[j], swv, sw);
                 }
                 if (__any_sync(kFull, s + gl + H * W < lim)) gather_run<F>(pairs, rec, min(s + gl + H * W, lim), lim, W, swv, sw);
             }
@@ -775,31 +819,7 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
             if (!heavy_mine) gather_run<F>(pairs, rec, s + gl, e, W, swv, sw);
 #endif
 
-            if constexpr (RG_SMEMREDUCE && W <= 16) {
-                // Transpose through shared memory: every lane parks its 2F partial sums (conflict-free rows of 32),
-                // then lane f of a group reads the W partials of field f with 128-bit loads and adds them up:
-                // 2F stores + W/2 vector loads + 2(W-1) adds instead of 14 shuffles with 2 selects and an add each.
-                float* red = red_buf[threadIdx.x >> 5];
-#pragma unroll
-                for (int f = 0; f < F; ++f) {
-                    red[f * kRedStride + lane] = swv[f];
-                    red[(F + f) * kRedStride + lane] = sw[f];
-                }
-                __syncwarp();
-                const int fo = gl < F ? gl : F - 1;                         // idle lanes read a valid row
-                const float4* pa = reinterpret_cast<const float4*>(red + fo * kRedStride + (lane & ~(W - 1)));
-                const float4* pb = reinterpret_cast<const float4*>(red + (F + fo) * kRedStride + (lane & ~(W - 1)));
-                float4 qa = pa[0], qb = pb[0];
-                a = (qa.x + qa.y) + (qa.z + qa.w);
-                b = (qb.x + qb.y) + (qb.z + qb.w);
-#pragma unroll
-                for (int k = 1; k < W / 4; ++k) {
-                    qa = pa[k]; qb = pb[k];
-                    a += (qa.x + qa.y) + (qa.z + qa.w);
-                    b += (qb.x + qb.y) + (qb.z + qb.w);
-                }
-                __syncwarp();
-            } else if constexpr (RG_TREDUCE && W >= 8) {
+            if constexpr (RG_TREDUCE && W >= 8) {
                 // plain butterfly down to 8 lanes, then reduce-scatter: lane f of the group gets field f
 #pragma unroll
                 for (int f = 0; f < F; ++f) {
@@ -839,6 +859,9 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
                 if (z == p.prod.slices[0].z_hi) q_hi = v;
             }
         }
+#if RG_ASYNCHEAD && RG_HEADBATCH
+        stage ^= 1;
+#endif
     }
     if constexpr (PSIG == 2) {
         if (owner) {
