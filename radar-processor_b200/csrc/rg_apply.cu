@@ -438,32 +438,6 @@ __device__ __forceinline__ float fast_div(float a, float b)
 #endif
 }
 
-#ifndef RG_ASYNCHEAD
-#define RG_ASYNCHEAD 1         // 1: the head of the NEXT level's row is copied global->shared with cp.async while this level is summed
-#endif
-// 8-byte asynchronous copy global -> shared (LDGSTS): no destination register, completion tracked per thread
-__device__ __forceinline__ void cp_async8(uint2* smem_dst, const uint2* gmem_src)
-{
-#ifndef RG_EMU
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
-#else
-    *smem_dst = *gmem_src;
-#endif
-}
-__device__ __forceinline__ void cp_async_commit()
-{
-#ifndef RG_EMU
-    asm volatile("cp.async.commit_group;");
-#endif
-}
-template <int N>
-__device__ __forceinline__ void cp_async_wait()          // all but the N most recent groups of this thread have landed
-{
-#ifndef RG_EMU
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-#endif
-}
-
 __device__ __forceinline__ void prefetch_l2(const void* ptr)
 {
 #ifndef RG_EMU
@@ -704,24 +678,6 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
     uint32_t s_next, e_next, s_next2, e_next2;
     bounds(p.lz_first, s_next, e_next);
     bounds(p.lz_first + 1, s_next2, e_next2);
-#if RG_ASYNCHEAD && RG_HEADBATCH
-    // Head staging: while level z is summed, every lane copies the first 2U-1 pairs it will need at level z+1 from
-    // global to its own shared-memory slots with cp.async (no registers held, nobody else reads the slots), so
-    // the gathers of a row start from a shared-memory read instead of a trip to L2.  Double-buffered by level parity.
-    constexpr int kHead = 2 * RG_UNROLL - 1;
-    __shared__ uint2 head_sm[2][kHead][kApplyThreads];
-    auto stage_head = [&](int stage, uint32_t bs, uint32_t be) {
-        if (W < 32 && be - bs > kHeavyRow) return;             // heavy rows are read by the whole warp from global
-#pragma unroll
-        for (int j = 0; j < kHead; ++j) {
-            const uint32_t q = bs + gl + j * W;
-            if (q < be) cp_async8(&head_sm[stage][j][threadIdx.x], pairs + q);
-        }
-    };
-    stage_head(0, s_next, e_next);
-    cp_async_commit();
-    int stage = 0;
-#endif
 
     size_t row = (size_t)p.lz_first * (size_t)p.ncol + (size_t)col - (size_t)p.ncol;
     for (int lz = p.lz_first; lz < p.lz_last; ++lz) {
@@ -730,17 +686,9 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
         s_next = s_next2;
         e_next = e_next2;
         bounds(lz + 2, s_next2, e_next2);
-#if RG_ASYNCHEAD && RG_HEADBATCH
-        stage_head(stage ^ 1, s_next, e_next);                 // level z+1 (bounds arrived an iteration ago)
-        cp_async_commit();
-#endif
 #if RG_PREFETCH > 0
         {   // pull the pair lines of level z+1 from HBM into L2: one 128-byte line (16 pairs) per lane of the group
-#if RG_ASYNCHEAD && RG_HEADBATCH
-            const uint32_t q = s_next + kHead * W + 16u * gl;  // the part the head staging does not cover
-#else
             const uint32_t q = s_next + 16u * gl;
-#endif
             if (q < e_next) prefetch_l2(pairs + q);
         }
 #endif
@@ -791,14 +739,8 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
                 constexpr int U = RG_UNROLL, H = 2 * U - 1, NV = Layout<F>::NV;
                 const uint32_t lim = heavy_mine ? s : e;               // heavy rows were summed by the whole warp
                 uint2 hp[H];
-#if RG_ASYNCHEAD
-                cp_async_wait<1>();                                    // this level's head has landed; the next one may still fly
-#pragma unroll
-                for (int j = 0; j < H; ++j) hp[j] = s + gl + j * W < lim ? head_sm[stage][j][threadIdx.x] : make_uint2(rec.null_gate, 0u);
-#else
 #pragma unroll
                 for (int j = 0; j < H; ++j) hp[j] = s + gl + j * W < lim ? __ldcs(pairs + s + gl + j * W) : make_uint2(rec.null_gate, 0u);
-#endif
                 {
                     float v[U][NV];
 #pragma unroll
@@ -859,9 +801,6 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
                 if (z == p.prod.slices[0].z_hi) q_hi = v;
             }
         }
-#if RG_ASYNCHEAD && RG_HEADBATCH
-        stage ^= 1;
-#endif
     }
     if constexpr (PSIG == 2) {
         if (owner) {
