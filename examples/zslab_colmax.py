@@ -58,11 +58,21 @@ def main():
     mine = [slabs[i] for i in D.shard_volumes(len(slabs), world, rank)]
     partial = torch.full((1, ny, nx), float("nan"), device="cuda")
     log = []
-    for z0, z1 in mine:
+    todo = list(mine)
+    while todo:
+        z0, z1 = todo.pop(0)
         t0 = time.perf_counter()
-        geom = rg.DeviceGeometry.build(*dgates, spec.grid_shape, spec.grid_limits, min_radius=spec.min_radius,
-                                       beam_factor=spec.beam_factor, weighting=spec.weighting, toa=spec.toa,
-                                       z_range=(z0, z1), ctx=ctx)
+        try:
+            geom = rg.DeviceGeometry.build(*dgates, spec.grid_shape, spec.grid_limits, min_radius=spec.min_radius,
+                                           beam_factor=spec.beam_factor, weighting=spec.weighting, toa=spec.toa,
+                                           z_range=(z0, z1), ctx=ctx)
+        except NotImplementedError:
+            # a slab table is indexed with 32 bits: more than 2^32-1 pairs -> halve the slab (the lowest levels are the densest)
+            if z1 - z0 < 2:
+                raise
+            zm = (z0 + z1) // 2
+            todo[:0] = [(z0, zm), (zm, z1)]
+            continue
         t_build = time.perf_counter() - t0
         t0 = time.perf_counter()
         res = rg.grid_fields(geom, [dfield], mask_invalid=True, want_grid=False, products=[rg.ColumnMax()], ctx=ctx)
@@ -78,7 +88,7 @@ def main():
     colmax = D.allreduce_nanmax(partial)                      # one NCCL all-reduce(max) across the ranks
     torch.cuda.synchronize()
 
-    out = {"spec": spec.name, "grid": list(spec.grid_shape), "slabs": len(slabs), "world": world,
+    out = {"spec": spec.name, "grid": list(spec.grid_shape), "slabs": len(log) if world == 1 else len(slabs), "world": world,
            "total_pairs": sum(s["pairs"] for s in log), "valid_pixels": int((~torch.isnan(colmax)).sum().item()),
            "colmax_sum": float(torch.nan_to_num(colmax).double().sum().item()), "per_slab": log}
     if args.check:

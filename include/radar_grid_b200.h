@@ -83,6 +83,8 @@ int rg_context_create(int32_t device, void* stream, rg_context** out);
 int rg_context_destroy(rg_context* ctx);
 int rg_context_set_stream(rg_context* ctx, void* stream);
 int rg_context_synchronize(rg_context* ctx);
+/* the cudaStream_t the context launches on (for event / stream interop with the caller's framework) */
+int rg_context_get_stream(const rg_context* ctx, void** stream);
 /* number of this library's kernels launched through the context so far (bench.py: gpu_launches) */
 int rg_context_kernel_launches(const rg_context* ctx, int64_t* count);
 /* options: "group_width" (0 = auto, 4/8/16/32 lanes per voxel column), "apply_variant" (0 = auto, 1 = lane-group

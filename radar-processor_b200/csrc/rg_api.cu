@@ -366,6 +366,14 @@ int rg_context_synchronize(rg_context* c)
     return RG_OK;
 }
 
+int rg_context_get_stream(const rg_context* c, void** stream)
+{
+    const Context* ctx = reinterpret_cast<const Context*>(c);
+    if (!ctx || !stream) return fail(RG_ERR_INVALID, "NULL argument");
+    *stream = (void*)ctx->stream;
+    return RG_OK;
+}
+
 int rg_context_kernel_launches(const rg_context* c, int64_t* count)
 {
     const Context* ctx = reinterpret_cast<const Context*>(c);

@@ -71,6 +71,7 @@ _PROTOTYPES = {
     "rg_context_destroy": (C.c_int, [C.c_void_p]),
     "rg_context_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rg_context_synchronize": (C.c_int, [C.c_void_p]),
+    "rg_context_get_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "rg_context_kernel_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "rg_context_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "rg_context_kernel_time": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
@@ -170,6 +171,11 @@ class Context:
     def synchronize(self):
         check(lib().rg_context_synchronize(self.handle))
 
+    def stream_ptr(self) -> int:
+        p = C.c_void_p()
+        check(lib().rg_context_get_stream(self.handle, C.byref(p)))
+        return int(p.value or 0)
+
     def kernel_launches(self) -> int:
         n = C.c_int64(0)
         check(lib().rg_context_kernel_launches(self.handle, C.byref(n)))
@@ -254,6 +260,33 @@ def is_device_array(x) -> bool:
     if hasattr(x, "__cuda_array_interface__") and not isinstance(x, np.ndarray):
         return bool(getattr(x, "is_cuda", True))
     return False
+
+
+class torch_stream_order:
+    """
+    Stream-order a device-buffer call with the caller's torch stream: the library's stream first waits for
+    everything already queued on torch's current stream (the inputs), and torch's current stream then waits for
+    the library's work (the outputs) — so torch code before and after the call needs no manual synchronisation.
+    No host synchronisation happens.
+    """
+
+    def __init__(self, ctx: "Context", active: bool):
+        self.ext = self.cur = None
+        if active:
+            import torch
+            self.cur = torch.cuda.current_stream(ctx.device)
+            if self.cur.cuda_stream != ctx.stream_ptr():
+                self.ext = torch.cuda.ExternalStream(ctx.stream_ptr(), device=ctx.device)
+
+    def __enter__(self):
+        if self.ext is not None:
+            self.ext.wait_stream(self.cur)
+        return self
+
+    def __exit__(self, *exc):
+        if self.ext is not None:
+            self.cur.wait_stream(self.ext)
+        return False
 
 
 def device_ptr(x) -> int:

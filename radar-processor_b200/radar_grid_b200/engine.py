@@ -70,9 +70,10 @@ class DeviceGeometry:
             ptrs = [N.host_ptr(a) for a in keep]
             n = keep[0].shape[0]
             space = N.RG_HOST
-        N.check(N.lib().rg_geometry_build(ctx.handle, ptrs[0], ptrs[1], ptrs[2], n, space, C.byref(spec),
-                                          float(radar_altitude), float(min_radius), float(beam_factor),
-                                          N.RG_W[weighting], float(toa), C.byref(h)))
+        with N.torch_stream_order(ctx, space == N.RG_DEVICE):
+            N.check(N.lib().rg_geometry_build(ctx.handle, ptrs[0], ptrs[1], ptrs[2], n, space, C.byref(spec),
+                                              float(radar_altitude), float(min_radius), float(beam_factor),
+                                              N.RG_W[weighting], float(toa), C.byref(h)))
         del keep
         return cls(h, ctx, grid_shape, grid_limits, z_range)
 
@@ -326,8 +327,9 @@ def run_products(grids: Sequence, grid_shape, grid_limits, products: Sequence, z
     if structs:
         gp = (C.c_void_p * F)(*[_ptr(g, device) for g in held])
         arr = (N.Product * len(structs))(*structs)
-        N.check(N.lib().rg_products(ctx.handle, C.byref(spec), F, gp, len(structs), arr,
-                                    N.RG_DEVICE if device else N.RG_HOST))
+        with N.torch_stream_order(ctx, device):
+            N.check(N.lib().rg_products(ctx.handle, C.byref(spec), F, gp, len(structs), arr,
+                                        N.RG_DEVICE if device else N.RG_HOST))
     return outs
 
 
@@ -445,7 +447,8 @@ def grid_fields(geom: DeviceGeometry, fields: Sequence, masks: Optional[Sequence
     parr = (N.Product * max(len(pstructs), 1))(*pstructs)
     args.rules = rarr
     args.products = parr
-    N.check(N.lib().rg_apply(ctx.handle, geom._h, C.byref(args), N.RG_DEVICE if device else N.RG_HOST))
+    with N.torch_stream_order(ctx, device):
+        N.check(N.lib().rg_apply(ctx.handle, geom._h, C.byref(args), N.RG_DEVICE if device else N.RG_HOST))
     return {"grids": grids, "products": pouts, "_keep": (fheld, mheld, rheld)}
 
 

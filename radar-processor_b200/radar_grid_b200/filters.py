@@ -235,8 +235,9 @@ class GridFilter:
                 src = src.to(torch.float32)
             out = torch.empty_like(src)
             bits = 32 if src.dtype == torch.float32 else 64
-            N.check(N.lib().rg_plane_filter(ctx.handle, N.device_ptr(src), N.device_ptr(out), src.numel(), bits, kind,
-                                            float(a), float(b), float(fill_value), N.RG_DEVICE))
+            with N.torch_stream_order(ctx, True):
+                N.check(N.lib().rg_plane_filter(ctx.handle, N.device_ptr(src), N.device_ptr(out), src.numel(), bits, kind,
+                                                float(a), float(b), float(fill_value), N.RG_DEVICE))
             return out
         src = np.asarray(grid)
         if src.dtype not in (np.float32, np.float64):
