@@ -103,3 +103,41 @@ def test_reference_order_and_fast_kernels_agree(case):
         alt = rg.grid_fields(dev, [data], masks=[mask], products=[rg.ColumnMax()])
         np.testing.assert_allclose(alt["grids"][0], exact, rtol=1e-5, atol=1e-4, equal_nan=True)
     dev.ctx.set_option("apply_variant", 0)
+
+
+def test_full_size_bit_exact_against_the_oracle_on_the_same_table(case):
+    """
+    BASELINE configs 1/2/3 at full size, bit for bit: the oracle (NumPy, the reference's arithmetic) applied to the
+    table the GPU built must equal the reference-order kernel — grids of every field, with and without the cfg2
+    RHOHV 0.8-1.0 QC filter — and COLMAX / CAPPI 4000 m / PPI 0.5 deg of those grids must equal the GPU products.
+    """
+    spec, gates, dev = case
+    fields = S.make_fields(S.SPECS["cfg3"] if spec.name == "cfg3" else S.SPECS["cfg2"], seed=1, gates=gates)
+    names = list(fields)[:2] if spec.name == "cfg3" else list(fields)          # DBZH (+ZDR | RHOHV)
+    indptr, idx, w = dev.export_csr()
+    data = [np.ma.getdata(fields[n]) for n in names]
+    masks = [np.ma.getmaskarray(fields[n]) for n in names]
+    got = rg.grid_fields(dev, data, masks=masks, reference_order=True)["grids"]
+    for n, g in zip(names, got):
+        want = O.apply_geometry(indptr, idx, w, spec.grid_shape, fields[n])
+        np.testing.assert_array_equal(g, want, err_msg=f"{spec.name} grid {n}")
+    # cfg2: GateFilter.exclude_below('RHOHV', 0.8).exclude_above('RHOHV', 1.0) as a fused gate mask
+    rho = np.ma.getdata(fields["RHOHV"]) if "RHOHV" in fields else None
+    if rho is not None:
+        excl = O.exclude_below(rho, 0.8) | O.exclude_above(rho, 1.0)
+        want = O.apply_geometry(indptr, idx, w, spec.grid_shape, fields["DBZH"], extra_masks=[excl])
+        rules = [rg.RangeRule(rho, lo=0.8), rg.RangeRule(rho, hi=1.0)]
+        got_qc = rg.grid_fields(dev, [np.ma.getdata(fields["DBZH"])], masks=[np.ma.getmaskarray(fields["DBZH"])],
+                                rules=rules, reference_order=True,
+                                products=[rg.ColumnMax(), rg.CAPPI(4000.0), rg.PPI(0.5), rg.PPI(0.5, "nearest")])
+        np.testing.assert_array_equal(got_qc["grids"][0], want, err_msg="QC-filtered grid")
+        np.testing.assert_array_equal(got_qc["products"][0][0], O.column_reduce("max", want))
+        np.testing.assert_array_equal(got_qc["products"][1][0], O.cappi(want, spec.grid_shape, spec.grid_limits, 4000.0))
+        np.testing.assert_array_equal(got_qc["products"][2][0], O.ppi(want, spec.grid_shape, spec.grid_limits, 0.5))
+        np.testing.assert_array_equal(got_qc["products"][3][0], O.ppi(want, spec.grid_shape, spec.grid_limits, 0.5, "nearest"))
+        # and the fast fused path agrees within the north-star tolerance, same mask
+        fast = rg.grid_fields(dev, [np.ma.getdata(fields["DBZH"])], masks=[np.ma.getmaskarray(fields["DBZH"])], rules=rules,
+                              products=[rg.ColumnMax(), rg.CAPPI(4000.0), rg.PPI(0.5)], want_grid=False)["products"]
+        for a, b in zip(fast, got_qc["products"][:3]):
+            np.testing.assert_array_equal(np.isnan(a), np.isnan(b))
+            np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-4, equal_nan=True)
