@@ -452,6 +452,56 @@ def grid_fields(geom: DeviceGeometry, fields: Sequence, masks: Optional[Sequence
     return {"grids": grids, "products": pouts, "_keep": (fheld, mheld, rheld)}
 
 
+class GeometryCache:
+    """
+    Device-side cache of neighbour tables keyed by (gate coordinates, grid, ROI parameters) — the reuse the reference
+    gets from ``save_geometry`` / ``load_geometry`` (geometry.py:94-150): a table is built once per radar and scan
+    strategy and applied to every volume.  Least-recently-used tables are freed when ``max_bytes`` of HBM is exceeded.
+    """
+
+    def __init__(self, max_bytes: int = 64 << 30, builder=None):
+        from collections import OrderedDict
+        self.max_bytes = int(max_bytes)
+        self._items = OrderedDict()
+        self._builder = builder or DeviceGeometry.build
+        self.hits = self.misses = 0
+
+    @staticmethod
+    def key(gate_x, gate_y, gate_z, grid_shape, grid_limits, **params) -> str:
+        import hashlib
+        h = hashlib.blake2b(digest_size=16)
+        for a in (gate_x, gate_y, gate_z):
+            h.update(np.ascontiguousarray(np.asarray(a), dtype=np.float32).tobytes())
+        h.update(repr((tuple(int(v) for v in grid_shape), tuple(tuple(float(v) for v in l) for l in grid_limits),
+                       sorted((k, (float(v) if isinstance(v, (int, float, np.floating, np.integer)) else v)) for k, v in params.items()))).encode())
+        return h.hexdigest()
+
+    def get(self, gate_x, gate_y, gate_z, grid_shape, grid_limits, **params) -> "DeviceGeometry":
+        k = self.key(gate_x, gate_y, gate_z, grid_shape, grid_limits, **params)
+        if k in self._items:
+            self._items.move_to_end(k)
+            self.hits += 1
+            return self._items[k]
+        self.misses += 1
+        geom = self._builder(gate_x, gate_y, gate_z, grid_shape, grid_limits, **params)
+        self._items[k] = geom
+        self._evict()
+        return geom
+
+    def bytes_held(self) -> int:
+        return sum(int(g.info["device_bytes"]) for g in self._items.values())
+
+    def _evict(self):
+        while len(self._items) > 1 and self.bytes_held() > self.max_bytes:
+            _, old = self._items.popitem(last=False)
+            old.close()
+
+    def clear(self):
+        for g in self._items.values():
+            g.close()
+        self._items.clear()
+
+
 class VolumePipeline:
     """
     Overlap the host<->device copies of consecutive volumes with the kernels of their neighbours.

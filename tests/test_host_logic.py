@@ -190,3 +190,32 @@ def test_product_code_never_imports_the_oracle_or_reads_the_reference():
                 assert not pat.search(text), f"{f} references the oracle / the reference tree"
     hdr = open(os.path.join(ROOT, "include", "radar_grid_b200.h")).read()
     assert "NO CPU fallback" in hdr
+
+
+def test_geometry_cache_keys_and_lru_eviction():
+    """GeometryCache: same inputs -> one build; any change of gates / grid / ROI parameters -> a new table; LRU eviction."""
+    built, closed = [], []
+
+    class FakeGeom:
+        def __init__(self, n):
+            self.info = {"device_bytes": n}
+        def close(self):
+            closed.append(self)
+
+    def builder(gx, gy, gz, shape, limits, **params):
+        g = FakeGeom(100)
+        built.append(g)
+        return g
+
+    cache = rg.GeometryCache(max_bytes=250, builder=builder)
+    gx, gy, gz = (np.arange(10, dtype=np.float32) + k for k in range(3))
+    a = cache.get(gx, gy, gz, (2, 3, 4), LIM, min_radius=250.0, weighting="barnes2")
+    assert cache.get(gx, gy, gz, (2, 3, 4), LIM, min_radius=250.0, weighting="barnes2") is a
+    assert (cache.hits, cache.misses, len(built)) == (1, 1, 1)
+    b = cache.get(gx, gy, gz, (2, 3, 4), LIM, min_radius=300.0, weighting="barnes2")          # ROI parameter changed
+    c = cache.get(gx + 1, gy, gz, (2, 3, 4), LIM, min_radius=250.0, weighting="barnes2")      # gates changed
+    assert len({id(a), id(b), id(c)}) == 3 and len(built) == 3
+    assert closed == [a] and cache.bytes_held() == 200                                        # 300 > 250: oldest freed
+    assert cache.get(gx, gy, gz, (2, 3, 5), LIM, min_radius=250.0, weighting="barnes2") is not a   # grid changed
+    cache.clear()
+    assert cache.bytes_held() == 0
