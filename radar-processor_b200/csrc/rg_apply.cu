@@ -9,19 +9,19 @@
 //   src/radar_grid/products.py:420-580     column_max / column_min / column_mean
 //
 // Data layout in HBM
-//   pairs   uint2[P]      {gate id, float32 weight bits}  — one 8-byte stream, read exactly once per apply
-//   indptr  uint32[V+1]   row v = (lz*ny + iy)*nx + ix
-//   records float[G][FP]  FP = 1/2/4/8 floats per gate: the F field values of a gate side by side, so a
-//                         single 4..32-byte gather serves every field; a masked value is the bit pattern
-//                         kMaskedBits.  The record array is small (<= 32 B * G) and is re-read ~P/G times:
-//                         it is meant to live in L2 while the pair stream goes past it with evict-first
-//                         loads.
-// Mapping
-//   A CTA owns 256/W consecutive columns (flattened iy*nx + ix); a group of W lanes owns one column and
-//   walks its levels bottom-up.  For one level the CTA's rows are consecutive CSR rows, so the pair
-//   stream is read in contiguous multi-KB runs.  Because a group sees every level of its column, the
-//   column products (running max, the two levels of a CAPPI/PPI blend) are kept in registers and written
-//   once: a products-only request never writes the 3-D grid.
+//   pairs   uint2[P]        {gate id, float32 weight bits} - one 8-byte stream, read exactly once per apply; every
+//                           row is sorted by gate id, i.e. it is a few runs of consecutive bins of the same ray
+//   indptr  uint32[V+1]     row v = (lz*ny + iy)*nx + ix
+//   records A float[G+1][FA], B float[G+1][FB]   the F field values of a gate: fields 0..3 in A, 4..7 in B; a masked
+//                           value is the bit pattern kMaskedBits; record G is all-masked (target of idle lanes).
+//                           The records are small (20 B * G for five fields) and re-read ~P/G times: they live in
+//                           L1/L2 while the pair stream goes past them with evict-first loads.
+// Mapping (apply_columns_kernel)
+//   A CTA owns a small 2-D patch of voxel columns; a group of W lanes owns one column and walks its levels bottom-up.
+//   Lane j of the group takes pairs j, j+W, ... of the row, so neighbouring lanes gather neighbouring gate records.
+//   Because a group sees every level of its column, the column products (running max, the two levels of a CAPPI /
+//   PPI blend) are kept on chip and written once: a products-only request never writes the 3-D grid.
+//   DESIGN.md section 6 has the measured history of every decision in this file.
 
 #include <math.h>
 
