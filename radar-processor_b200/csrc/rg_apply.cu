@@ -732,7 +732,50 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
                 heavy_mine = false;
             }
 
-#if RG_HEADBATCH
+#if RG_HEADBATCH == 2
+            {
+                // Head of the row, sized exactly: m = the largest number of pairs any lane of the warp has to take
+                // (one warp reduction), then ONE code path per m <= 7 that issues all m pair loads together and
+                // gathers in chunks of at most U.  No slot is executed that no lane needs.
+                constexpr int U = RG_UNROLL, H = 2 * U - 1, NV = Layout<F>::NV;
+                const uint32_t lim = heavy_mine ? s : e;               // heavy rows were summed by the whole warp
+                const uint32_t need = lim > s + gl ? (lim - s - gl + W - 1) / W : 0u;
+                const uint32_t m = __reduce_max_sync(kFull, need);
+                auto head = [&](auto mm) {
+                    constexpr int M = decltype(mm)::value;
+                    uint2 hp[M];
+#pragma unroll
+                    for (int j = 0; j < M; ++j) hp[j] = (uint32_t)j < need ? __ldcs(pairs + s + gl + j * W) : make_uint2(rec.null_gate, 0u);
+                    constexpr int C0 = M < U ? M : U;
+                    {
+                        float v[C0][NV];
+#pragma unroll
+                        for (int j = 0; j < C0; ++j) load_record<F>(rec, hp[j].x, v[j]);
+#pragma unroll
+                        for (int j = 0; j < C0; ++j) accumulate<F, NV>(__uint_as_float(hp[j].y), v[j], swv, sw);
+                    }
+                    if constexpr (M > U) {
+                        float v[M - U][NV];
+#pragma unroll
+                        for (int j = 0; j < M - U; ++j) load_record<F>(rec, hp[U + j].x, v[j]);
+#pragma unroll
+                        for (int j = 0; j < M - U; ++j) accumulate<F, NV>(__uint_as_float(hp[U + j].y), v[j], swv, sw);
+                    }
+                };
+                static_assert(H == 7 || H == 5 || H == 3, "head sizes are written out below");
+                switch (m < (uint32_t)H ? m : (uint32_t)H) {
+                    case 0: break;
+                    case 1: head(std::integral_constant<int, 1>{}); break;
+                    case 2: head(std::integral_constant<int, 2>{}); break;
+                    case 3: head(std::integral_constant<int, 3>{}); break;
+                    case 4: if constexpr (H >= 4) head(std::integral_constant<int, 4>{}); break;
+                    case 5: if constexpr (H >= 5) head(std::integral_constant<int, 5>{}); break;
+                    case 6: if constexpr (H >= 6) head(std::integral_constant<int, 6>{}); break;
+                    default: if constexpr (H >= 7) head(std::integral_constant<int, 7>{}); break;
+                }
+                if (m > (uint32_t)H) gather_run<F>(pairs, rec, min(s + gl + H * W, lim), lim, W, swv, sw);
+            }
+#elif RG_HEADBATCH
             {
                 // Head of the row: the pair loads of the first 2U-1 slots of every lane are issued together, so
                 // that the second batch of gathers does not wait for another trip to L2 (most rows fit entirely).
