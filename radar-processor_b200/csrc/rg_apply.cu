@@ -567,7 +567,8 @@ __device__ __forceinline__ void accumulate(float w, const float (&v)[NV], float 
 }
 
 #ifndef RG_HEADBATCH
-#define RG_HEADBATCH 1         // 1: issue the pair loads of the first 2U-1 slots of a row together
+#define RG_HEADBATCH 2         // 1: the pair loads of the first 2U-1 slots of a row are issued together; 2: same, and exactly
+                               //    as many slots as the longest row of the warp needs (one code path per count)
 #endif
 #ifndef RG_TILE2D
 #define RG_TILE2D 1            // CTA = 8 x 4 patch of columns (1) or 32 consecutive columns (0)
