@@ -150,6 +150,9 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     spec = S.SPECS[args.workload]
+    if os.environ.get("RG_BENCH_FIELDS"):                      # kernel experiments only: first k fields of the workload
+        import dataclasses
+        spec = dataclasses.replace(spec, fields=spec.fields[:int(os.environ["RG_BENCH_FIELDS"])])
     F = len(spec.fields)
     nz, ny, nx = spec.grid_shape
     V, ncol, G = nz * ny * nx, ny * nx, spec.n_gates

@@ -164,6 +164,10 @@ class Context:
         h = C.c_void_p()
         check(lib().rg_context_create(self.device, C.c_void_p(stream) if stream else None, C.byref(h)))
         self.handle = h
+        # kernel A/B knobs for tests and experiments (rg_context_set_option); unset = the library's own choice
+        for env, key in (("RG_GROUP_WIDTH", "group_width"), ("RG_APPLY_VARIANT", "apply_variant")):
+            if os.environ.get(env):
+                self.set_option(key, int(os.environ[env]))
 
     def set_stream(self, stream: int | None):
         check(lib().rg_context_set_stream(self.handle, C.c_void_p(stream) if stream else None))
