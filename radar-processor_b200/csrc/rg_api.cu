@@ -139,6 +139,7 @@ void free_geometry(Geometry* g)
     cudaFree(g->indptr);
     cudaFree(g->pairs);
     cudaFree(g->sell);
+    for (auto& qc : g->quad) { cudaFree(qc.quads); cudaFree(qc.ptr); }
     cudaFree(g->slice_base);
     cudaFree(g->x_ax);
     cudaFree(g->y_ax);

@@ -621,10 +621,13 @@ __device__ __forceinline__ void gather_run(const uint2* __restrict__ pairs, cons
 
 // PSIG: 0 = no products, 1 = any product list (op list over shared-memory state), 2 = the operational request
 // "COLMAX and/or one level pick/blend (CAPPI)" with its three state words in registers.
-template <int F, int W, int PSIG>
+// IL: the pairs come from the warp-slice copy of the table (one coalesced 256-byte load per slot, no per-lane row
+// bounds, the slot count of a level is warp-uniform) instead of the CSR copy.
+template <int F, int W, int PSIG, bool IL>
 __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_kernel(const __grid_constant__ ApplyParams p)
 {
     constexpr bool PROD = PSIG == 1;
+    static_assert(!IL || RG_TILE2D == 1, "the warp-slice copy assumes the groups of a warp are adjacent in x");
     static_assert(W >= F || W == 32, "one lane per field in the epilogue");
     constexpr unsigned kFull = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
@@ -642,6 +645,7 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
 #else
     const int64_t col = (int64_t)blockIdx.x * (kApplyThreads / W) + threadIdx.x / W;
     const bool col_ok = col < p.ncol;
+    const int cx = 0, cy = 0;                                  // only used by the warp-slice path (2-D tiles)
 #endif
     const bool owner = col_ok && gl < F;                       // lane gl finishes field gl
 
@@ -668,9 +672,20 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
     float* const out = owner ? p.grid_out[gl] : nullptr;
     // Row bounds run two levels ahead of the sums, so that the L2 prefetch of level z+1 (issued while level z is
     // summed) never waits for the bounds load it depends on.
+    // IL: (bs, be) are the slice's two quad_ptr words, identical in all lanes of the warp
+    const uint2* __restrict__ quads = p.quads;
+    const uint32_t* __restrict__ quad_ptr = p.quad_ptr;
+    const int qx = cx / (32 / W);
+    const bool slice_ok = cy < p.ny && qx < p.quads_x;
     auto bounds = [&](int lz, uint32_t& bs, uint32_t& be) {
         bs = be = 0;
-        if (col_ok && lz < p.lz_last) {
+        if constexpr (IL) {
+            if (slice_ok && lz < p.lz_last) {
+                const size_t q = ((size_t)lz * (size_t)p.ny + (size_t)cy) * (size_t)p.quads_x + (size_t)qx;
+                bs = __ldg(quad_ptr + q);
+                be = __ldg(quad_ptr + q + 1);
+            }
+        } else if (col_ok && lz < p.lz_last) {
             const size_t r = (size_t)lz * (size_t)p.ncol + (size_t)col;
             bs = __ldg(indptr + r);
             be = __ldg(indptr + r + 1);
@@ -688,13 +703,19 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
         e_next = e_next2;
         bounds(lz + 2, s_next2, e_next2);
 #if RG_PREFETCH > 0
-        {   // pull the pair lines of level z+1 from HBM into L2: one 128-byte line (16 pairs) per lane of the group
+        if constexpr (IL) {   // level z+1's slots are contiguous: one 128-byte line per lane
+            const uint32_t l0 = (s_next >> 1) * 2u + (uint32_t)lane;
+            if (l0 < (e_next >> 1) * 2u) prefetch_l2(quads + (size_t)l0 * 16);
+        } else {   // pull the pair lines of level z+1 from HBM into L2: one 128-byte line (16 pairs) per lane of the group
             const uint32_t q = s_next + 16u * gl;
             if (q < e_next) prefetch_l2(pairs + q);
         }
 #endif
 
-        const uint32_t len = e - s;
+        // IL: m slots for the whole warp, hv = some row of the slice is heavy (kept out of the slice copy)
+        const uint32_t il_p0 = s >> 1, il_m = (e >> 1) - il_p0;
+        const bool il_hv = s & 1u;
+        const uint32_t len = IL ? il_m + (il_hv ? 1u : 0u) : e - s;
         float a = 0.f, b = 0.f;
         // warps whose four rows are all empty (outside the radar range, above the highest sweep) skip the sums
         if (__any_sync(kFull, len != 0)) {
@@ -702,7 +723,15 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
 #pragma unroll
             for (int f = 0; f < F; ++f) { swv[f] = 0.f; sw[f] = 0.f; }
 
-            bool heavy_mine = len > kHeavyRow;
+            uint32_t cs = s, ce = e;                           // CSR bounds of this lane's row
+            if constexpr (IL) {
+                cs = ce = 0;
+                if (il_hv && col_ok) {
+                    cs = __ldg(indptr + row);
+                    ce = __ldg(indptr + row + 1);
+                }
+            }
+            bool heavy_mine = ce - cs > kHeavyRow;
             if constexpr (W < 32) {
                 // Rows far longer than the group is wide (the voxels next to the radar see the first gates
                 // of every ray) are summed by the whole warp, then handed back to the owning group.
@@ -710,8 +739,8 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
                 while (heavy) {
                     const int src = __ffs(heavy) - 1;
                     heavy &= heavy - 1;
-                    const uint32_t hs = __shfl_sync(kFull, s, src);
-                    const uint32_t he = __shfl_sync(kFull, e, src);
+                    const uint32_t hs = __shfl_sync(kFull, cs, src);
+                    const uint32_t he = __shfl_sync(kFull, ce, src);
                     float hwv[F], hw[F];
 #pragma unroll
                     for (int f = 0; f < F; ++f) { hwv[f] = 0.f; hw[f] = 0.f; }
@@ -740,13 +769,23 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
                 // gathers in chunks of at most U.  No slot is executed that no lane needs.
                 constexpr int U = RG_UNROLL, H = 2 * U - 1, NV = Layout<F>::NV;
                 const uint32_t lim = heavy_mine ? s : e;               // heavy rows were summed by the whole warp
-                const uint32_t need = lim > s + gl ? (lim - s - gl + W - 1) / W : 0u;
-                const uint32_t m = __reduce_max_sync(kFull, need);
+                uint32_t need = 0, m;
+                const uint2* il_base = nullptr;
+                if constexpr (IL) {
+                    m = il_m;                                          // warp-uniform by construction
+                    il_base = quads + (size_t)il_p0 * 32 + lane;
+                } else {
+                    need = lim > s + gl ? (lim - s - gl + W - 1) / W : 0u;
+                    m = __reduce_max_sync(kFull, need);
+                }
                 auto head = [&](auto mm) {
                     constexpr int M = decltype(mm)::value;
                     uint2 hp[M];
 #pragma unroll
-                    for (int j = 0; j < M; ++j) hp[j] = (uint32_t)j < need ? __ldcs(pairs + s + gl + j * W) : make_uint2(rec.null_gate, 0u);
+                    for (int j = 0; j < M; ++j) {
+                        if constexpr (IL) hp[j] = __ldcs(il_base + j * 32);
+                        else hp[j] = (uint32_t)j < need ? __ldcs(pairs + s + gl + j * W) : make_uint2(rec.null_gate, 0u);
+                    }
                     constexpr int C0 = M < U ? M : U;
                     {
                         float v[C0][NV];
@@ -774,9 +813,13 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
                     case 6: if constexpr (H >= 6) head(std::integral_constant<int, 6>{}); break;
                     default: if constexpr (H >= 7) head(std::integral_constant<int, 7>{}); break;
                 }
-                if (m > (uint32_t)H) gather_run<F>(pairs, rec, min(s + gl + H * W, lim), lim, W, swv, sw);
+                if (m > (uint32_t)H) {
+                    if constexpr (IL) gather_run<F>(il_base + H * 32, rec, 0u, (m - (uint32_t)H) * 32u, 32u, swv, sw);
+                    else gather_run<F>(pairs, rec, min(s + gl + H * W, lim), lim, W, swv, sw);
+                }
             }
 #elif RG_HEADBATCH
+            static_assert(!IL, "the warp-slice path is written for RG_HEADBATCH 2");
             {
                 // Head of the row: the pair loads of the first 2U-1 slots of every lane are issued together, so
                 // that the second batch of gathers does not wait for another trip to L2 (most rows fit entirely).
@@ -802,6 +845,7 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
                 if (__any_sync(kFull, s + gl + H * W < lim)) gather_run<F>(pairs, rec, min(s + gl + H * W, lim), lim, W, swv, sw);
             }
 #else
+            static_assert(!IL, "the warp-slice path is written for RG_HEADBATCH 2");
             if (!heavy_mine) gather_run<F>(pairs, rec, s + gl, e, W, swv, sw);
 #endif
 
@@ -1133,9 +1177,17 @@ static void launch_columns(Context* ctx, const ApplyParams& p)
     const ProductParams& pp = p.prod;
     const bool simple = pp.any && !pp.cmin_on && !pp.cmean_on && pp.n_slices <= 1 &&
                         (pp.n_slices == 0 || pp.slices[0].kind == RG_PROD_LEVEL) && ctx->apply_variant != 3;
-    if (!pp.any) apply_columns_kernel<F, W, 0><<<blocks, kApplyThreads, 0, ctx->stream>>>(p);
-    else if (simple) apply_columns_kernel<F, W, 2><<<blocks, kApplyThreads, 0, ctx->stream>>>(p);
-    else apply_columns_kernel<F, W, 1><<<blocks, kApplyThreads, smem, ctx->stream>>>(p);
+    if (p.quads != nullptr) {
+#if RG_TILE2D
+        if (!pp.any) apply_columns_kernel<F, W, 0, true><<<blocks, kApplyThreads, 0, ctx->stream>>>(p);
+        else if (simple) apply_columns_kernel<F, W, 2, true><<<blocks, kApplyThreads, 0, ctx->stream>>>(p);
+        else apply_columns_kernel<F, W, 1, true><<<blocks, kApplyThreads, smem, ctx->stream>>>(p);
+        return;
+#endif
+    }
+    if (!pp.any) apply_columns_kernel<F, W, 0, false><<<blocks, kApplyThreads, 0, ctx->stream>>>(p);
+    else if (simple) apply_columns_kernel<F, W, 2, false><<<blocks, kApplyThreads, 0, ctx->stream>>>(p);
+    else apply_columns_kernel<F, W, 1, false><<<blocks, kApplyThreads, smem, ctx->stream>>>(p);
 }
 
 template <int F>
@@ -1214,16 +1266,29 @@ int launch_apply(Context* ctx, const Geometry* g, const ApplyParams& p, bool ref
         return RG_OK;
     }
     const int W = pick_group_width(ctx, g, p.n_fields);
+    ApplyParams q = p;
+    q.quads = nullptr;
+    q.quad_ptr = nullptr;
+    q.quads_x = 0;
+#if RG_TILE2D && RG_HEADBATCH == 2
+    if (ctx->apply_variant == 4) {                      // pairs from the warp-slice copy (built on first use)
+        const Geometry::QuadCopy* qc = nullptr;
+        RG_TRY(ensure_quads(ctx, const_cast<Geometry*>(g), W, &qc));
+        q.quads = qc->quads;
+        q.quad_ptr = qc->ptr;
+        q.quads_x = qc->quads_x;
+    }
+#endif
     timer_begin(ctx, kTimerApply);
-    switch (p.n_fields) {
-        case 1: launch_columns_w<1>(ctx, p, W); break;
-        case 2: launch_columns_w<2>(ctx, p, W); break;
-        case 3: launch_columns_w<3>(ctx, p, W); break;
-        case 4: launch_columns_w<4>(ctx, p, W); break;
-        case 5: launch_columns_w<5>(ctx, p, W); break;
-        case 6: launch_columns_w<6>(ctx, p, W); break;
-        case 7: launch_columns_w<7>(ctx, p, W); break;
-        case 8: launch_columns_w<8>(ctx, p, W); break;
+    switch (q.n_fields) {
+        case 1: launch_columns_w<1>(ctx, q, W); break;
+        case 2: launch_columns_w<2>(ctx, q, W); break;
+        case 3: launch_columns_w<3>(ctx, q, W); break;
+        case 4: launch_columns_w<4>(ctx, q, W); break;
+        case 5: launch_columns_w<5>(ctx, q, W); break;
+        case 6: launch_columns_w<6>(ctx, q, W); break;
+        case 7: launch_columns_w<7>(ctx, q, W); break;
+        case 8: launch_columns_w<8>(ctx, q, W); break;
         default: return fail(RG_ERR_INVALID, "n_fields must be 1..8");
     }
     timer_end(ctx, kTimerApply);

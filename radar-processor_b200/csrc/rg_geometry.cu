@@ -491,6 +491,63 @@ __global__ void __launch_bounds__(128) sell_fill_kernel(const uint32_t* __restri
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Warp-slice copy of the table for the column-group apply kernel (see rg_internal.cuh / rg_apply.cu).
+// Rows longer than kHeavyRow stay out of it (the kernel sums them from the CSR copy with the whole warp).
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) quad_count_kernel(const uint32_t* __restrict__ indptr, int nx, int64_t n_slices, int R, int W,
+                                                         int quads_x, uint32_t heavy_len, uint32_t* __restrict__ counts,
+                                                         uint8_t* __restrict__ heavy)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_slices) return;
+    const int64_t line = q / quads_x;                          // lz * ny + cy
+    const int qx = (int)(q - line * quads_x);
+    uint32_t m = 0;
+    uint8_t hv = 0;
+    for (int k = 0; k < R; ++k) {
+        const int cx = qx * R + k;
+        if (cx >= nx) break;
+        const size_t row = (size_t)line * (size_t)nx + (size_t)cx;
+        const uint32_t len = indptr[row + 1] - indptr[row];
+        if (len > heavy_len) hv = 1;
+        else m = max(m, (len + (uint32_t)W - 1u) / (uint32_t)W);
+    }
+    counts[q] = m;
+    heavy[q] = hv;
+}
+
+__global__ void __launch_bounds__(128) quad_fill_kernel(const uint32_t* __restrict__ indptr, const uint2* __restrict__ pairs, int nx,
+                                                        int64_t n_slices, int R, int W, int quads_x, uint32_t heavy_len,
+                                                        const uint32_t* __restrict__ offs, const uint32_t* __restrict__ counts,
+                                                        const uint8_t* __restrict__ heavy, uint32_t null_gate,
+                                                        uint2* __restrict__ quads, uint32_t* __restrict__ quad_ptr)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (q >= n_slices) return;
+    const int64_t line = q / quads_x;
+    const int qx = (int)(q - line * quads_x);
+    const uint32_t m = counts[q], o = offs[q];
+    if (lane == 0) {
+        quad_ptr[q] = (o << 1) | heavy[q];
+        if (q == n_slices - 1) quad_ptr[n_slices] = (o + m) << 1;
+    }
+    const int cx = qx * R + lane / W, k0 = lane % W;
+    uint32_t s = 0, len = 0;
+    if (cx < nx) {
+        const size_t row = (size_t)line * (size_t)nx + (size_t)cx;
+        s = indptr[row];
+        len = indptr[row + 1] - s;
+        if (len > heavy_len) len = 0;
+    }
+    uint2* dst = quads + (size_t)o * 32 + lane;
+    for (uint32_t j = 0; j < m; ++j) {
+        const uint32_t k = j * (uint32_t)W + (uint32_t)k0;
+        dst[(size_t)j * 32] = k < len ? pairs[s + k] : make_uint2(null_gate, 0u);
+    }
+}
+
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
@@ -549,6 +606,53 @@ int build_sell(Context* ctx, Geometry* g)
     }
     RG_CUDA(cudaStreamSynchronize(ctx->stream));
     g->info.device_bytes = (int64_t)(((size_t)g->n_rows + 1) * 4 + (size_t)g->n_pairs * 8 + (size_t)total * 8 + ((size_t)n_slices + 1) * 4);
+    return RG_OK;
+}
+
+int ensure_quads(Context* ctx, Geometry* g, int W, const Geometry::QuadCopy** out)
+{
+    const int slot = W == 4 ? 0 : W == 8 ? 1 : W == 16 ? 2 : 3;
+    std::lock_guard<std::mutex> lock(g->quad_mu);
+    Geometry::QuadCopy& qc = g->quad[slot];
+    *out = &qc;
+    if (qc.ptr != nullptr) return RG_OK;
+    const int R = 32 / W, nx = g->grid.nx, ny = g->grid.ny;
+    const int quads_x = (nx + R - 1) / R;
+    const int64_t n_slices = (int64_t)g->n_levels * ny * quads_x;
+    // the kernel hands rows longer than kHeavyRow to the whole warp; a 32-lane group IS the whole warp
+    const uint32_t heavy_len = W == 32 ? 0xFFFFFFFFu : kHeavyRow;
+    DevBuf<uint32_t> counts, offs, qptr;
+    DevBuf<uint8_t> heavy;
+    DevBuf<unsigned long long> tmp;
+    RG_CUDA(qptr.alloc((size_t)n_slices + 1));
+    RG_CUDA(cudaMemsetAsync(qptr.p, 0, ((size_t)n_slices + 1) * sizeof(uint32_t), ctx->stream));
+    RG_CUDA(counts.alloc((size_t)n_slices));
+    RG_CUDA(offs.alloc((size_t)n_slices + 1));
+    RG_CUDA(heavy.alloc((size_t)n_slices));
+    RG_CUDA(tmp.alloc((size_t)(n_slices / kScanTile + 4)));
+    if (n_slices > 0) {
+        quad_count_kernel<<<(unsigned)((n_slices + 255) / 256), 256, 0, ctx->stream>>>(g->indptr, nx, n_slices, R, W, quads_x, heavy_len,
+                                                                                      counts.p, heavy.p);
+        ctx->launches++;
+        RG_CUDA(cudaGetLastError());
+    }
+    uint64_t total = 0;
+    RG_TRY(exclusive_scan_u32(ctx, counts.p, offs.p, n_slices, tmp.p, &total));
+    if (total >= (1ull << 31)) return fail(RG_ERR_UNSUPPORTED, "warp-slice copy of the table exceeds 2^31 slots; use more z-slabs");
+    DevBuf<uint2> quads;
+    RG_CUDA(quads.alloc((size_t)total * 32));
+    if (n_slices > 0) {
+        quad_fill_kernel<<<(unsigned)((n_slices + 3) / 4), 128, 0, ctx->stream>>>(g->indptr, g->pairs, nx, n_slices, R, W, quads_x, heavy_len,
+                                                                                 offs.p, counts.p, heavy.p, (uint32_t)g->n_gates, quads.p, qptr.p);
+        ctx->launches++;
+        RG_CUDA(cudaGetLastError());
+    }
+    RG_CUDA(cudaStreamSynchronize(ctx->stream));
+    qc.quads = quads.p; quads.p = nullptr;
+    qc.ptr = qptr.p; qptr.p = nullptr;
+    qc.n_slots = (int64_t)total;
+    qc.quads_x = quads_x;
+    g->info.device_bytes += (int64_t)((size_t)total * 32 * sizeof(uint2) + ((size_t)n_slices + 1) * sizeof(uint32_t));
     return RG_OK;
 }
 

@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -56,6 +57,18 @@ struct Geometry {
     uint2* sell = nullptr;               // [n_sell]
     uint32_t* slice_base = nullptr;      // [n_levels * slices_per_level + 1]
     int64_t n_sell = 0, slices_per_level = 0;
+    // Warp-slice copy for the column-group kernel: the rows of the 32/W adjacent columns one warp sums at one level
+    // form a slice; slot j of a slice holds pairs [jW, jW+W) of each of its rows, lane order, idle entries filled
+    // with the all-masked record.  One slot is one 256-byte coalesced load of the warp.
+    // One copy per group width in use (W = 4, 8, 16, 32 -> index 0..3), built on first use under quad_mu and kept
+    // until the table is destroyed, so that contexts on other streams can share it.
+    struct QuadCopy {
+        uint2* quads = nullptr;          // [n_slots][32]
+        uint32_t* ptr = nullptr;         // [n_levels * ny * quads_x + 1]: (first slot << 1) | slice has a heavy row
+        int64_t n_slots = 0;
+        int32_t quads_x = 0;
+    } quad[4];
+    std::mutex quad_mu;
     float* x_ax = nullptr;               // [nx]   float32 linspace axes (reference compute.py:184-186)
     float* y_ax = nullptr;               // [ny]
     float* z_ax = nullptr;               // [nz]   (full grid)
@@ -144,6 +157,9 @@ struct ApplyParams {
     const uint2* sell;                    // interleaved copy of the table (thread-per-column kernel)
     const uint32_t* slice_base;
     int64_t slices_per_level;
+    const uint2* quads;                   // warp-slice copy of the table (column-group kernel)
+    const uint32_t* quad_ptr;
+    int32_t quads_x;
     uint32_t null_gate;                   // index of the all-masked record (= n_gates)
     unsigned long long tex_a, tex_b;      // texture objects over records / records_b (RG_TEX builds)
     int64_t ncol;                         // ny*nx
@@ -191,6 +207,7 @@ int build_geometry_device(Context* ctx, const float* gx, const float* gy, const 
                           double toa, Geometry* out);
 int finalize_geometry_stats(Context* ctx, Geometry* g);
 int build_sell(Context* ctx, Geometry* g);
+int ensure_quads(Context* ctx, Geometry* g, int W, const Geometry::QuadCopy** out);
 int exclusive_scan_u32(Context* ctx, const uint32_t* in, uint32_t* out, int64_t n, unsigned long long* tmp, uint64_t* total_host);
 void linspace_f32(double start, double stop, int num, float* out);
 
