@@ -87,8 +87,10 @@ int rg_context_synchronize(rg_context* ctx);
 int rg_context_get_stream(const rg_context* ctx, void** stream);
 /* number of this library's kernels launched through the context so far (bench.py: gpu_launches) */
 int rg_context_kernel_launches(const rg_context* ctx, int64_t* count);
-/* options: "group_width" (0 = auto, 4/8/16/32 lanes per voxel column), "apply_variant" (0 = auto, 1 = lane-group
- * kernel, 2 = thread-per-column kernel over the interleaved table copy, 3 = lane-group kernel with the generic product path),
+/* options: "group_width" (0 = auto, 4/8/16/32 lanes per voxel column), "apply_variant" (0 = auto: lane-group
+ * kernel, pairs from the warp-slice copy of the table when two or more fields are gridded, else from the CSR copy;
+ * 1 = lane-group kernel over the CSR copy; 2 = thread-per-column kernel over the interleaved table copy; 3 = lane-group
+ * kernel with the generic product path; 4 = lane-group kernel over the warp-slice copy),
  * "timing" (1 = record CUDA events around every pack / apply launch, read with rg_context_kernel_time),
  * "sort_rows" (default 1: rg_geometry_build orders every row by gate id) */
 int rg_context_set_option(rg_context* ctx, const char* key, int64_t value);

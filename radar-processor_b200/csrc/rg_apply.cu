@@ -491,6 +491,40 @@ __device__ __forceinline__ void group8_reduce_scatter(const float (&swv)[F], con
     b = (up ? s_w[1] : s_w[0]) + __shfl_xor_sync(kFull, up ? s_w[0] : s_w[1], 1);
 }
 
+// Same idea for groups of 4 lanes: two halving exchanges; lane g ends up with the totals of field g and, when there
+// are more than four fields, of field g + 4.
+template <int F, int NO>
+__device__ __forceinline__ void group4_reduce_scatter(const float (&swv)[F], const float (&sw)[F], int gl, float (&a)[NO], float (&b)[NO])
+{
+    constexpr unsigned kFull = 0xFFFFFFFFu;
+    float u_wv[8], u_w[8];
+#pragma unroll
+    for (int f = 0; f < 8; ++f) { u_wv[f] = f < F ? swv[f] : 0.f; u_w[f] = f < F ? sw[f] : 0.f; }
+    // step 1 (lane distance 2): units {0,1,4,5} stay in the lower pair of lanes, {2,3,6,7} in the upper pair
+    float t_wv[4], t_w[4];
+    {
+        const bool up = gl & 2;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int lo = j < 2 ? j : j + 2, hi = lo + 2;       // (0,2) (1,3) (4,6) (5,7)
+            if (lo < F) {
+                t_wv[j] = (up ? u_wv[hi] : u_wv[lo]) + __shfl_xor_sync(kFull, up ? u_wv[lo] : u_wv[hi], 2);
+                t_w[j] = (up ? u_w[hi] : u_w[lo]) + __shfl_xor_sync(kFull, up ? u_w[lo] : u_w[hi], 2);
+            } else {
+                t_wv[j] = 0.f; t_w[j] = 0.f;
+            }
+        }
+    }
+    // step 2 (lane distance 1): even unit of each pair to the even lane
+    const bool up = gl & 1;
+    a[0] = (up ? t_wv[1] : t_wv[0]) + __shfl_xor_sync(kFull, up ? t_wv[0] : t_wv[1], 1);
+    b[0] = (up ? t_w[1] : t_w[0]) + __shfl_xor_sync(kFull, up ? t_w[0] : t_w[1], 1);
+    if constexpr (NO > 1) {
+        a[1] = (up ? t_wv[3] : t_wv[2]) + __shfl_xor_sync(kFull, up ? t_wv[2] : t_wv[3], 1);
+        b[1] = (up ? t_w[3] : t_w[2]) + __shfl_xor_sync(kFull, up ? t_w[2] : t_w[3], 1);
+    }
+}
+
 template <int F>
 struct Layout {
     static constexpr int FP = F == 1 ? 1 : F == 2 ? 2 : F <= 4 ? 4 : 8;
@@ -570,6 +604,11 @@ __device__ __forceinline__ void accumulate(float w, const float (&v)[NV], float 
 #define RG_HEADBATCH 2         // 1: the pair loads of the first 2U-1 slots of a row are issued together; 2: same, and exactly
                                //    as many slots as the longest row of the warp needs (one code path per count)
 #endif
+#ifndef RG_QSMEM
+#define RG_QSMEM 1             // 1: when a lane owns two fields, the COLMAX / level-pick state of the PSIG 2 path lives in shared
+                               //    memory and the grid pointers are re-read from the parameter bank at the store (fewer
+                               //    registers live across the gathers; measured: 0.82 -> 0.71 ms at five fields, W = 4)
+#endif
 #ifndef RG_TILE2D
 #define RG_TILE2D 1            // CTA = 8 x 4 patch of columns (1) or 32 consecutive columns (0)
 #endif
@@ -628,7 +667,9 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
 {
     constexpr bool PROD = PSIG == 1;
     static_assert(!IL || RG_TILE2D == 1, "the warp-slice copy assumes the groups of a warp are adjacent in x");
-    static_assert(W >= F || W == 32, "one lane per field in the epilogue");
+    // lane gl of a group finishes field gl and, in groups narrower than the field count, field gl + W as well
+    constexpr int NO = W < F ? 2 : 1;
+    static_assert(W * NO >= F, "every field needs an owner lane");
     constexpr unsigned kFull = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
     const int gl = threadIdx.x & (W - 1);                      // lane within the column group
@@ -654,9 +695,19 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
     const RecSrc rec{p.records, p.records_b, p.tex_a, p.tex_b, p.null_gate};
 
     // PSIG 2: running max and the two captured levels in registers
-    float q_max = __uint_as_float(kCanonNaN), q_lo = q_max, q_hi = q_max;
-    // per-lane product state (one field per owner lane) lives in shared memory: [word][thread]
+    constexpr bool QS = RG_QSMEM && NO > 1;    // two fields per owner lane: the registers are needed for the gathers
+    // ... in shared memory ([word][k][thread]): touched once per level by the owner lanes, and out of the way of the
+    // registers the gathers need
     extern __shared__ float sm_state[];
+    float* const q_state = sm_state;           // dynamic shared memory: 3 * NO words per thread (launch_columns)
+    if constexpr (PSIG == 2 && QS) {
+#pragma unroll
+        for (int i = 0; i < 3 * NO; ++i) q_state[i * kApplyThreads + threadIdx.x] = __uint_as_float(kCanonNaN);
+    }
+    float q_max[NO], q_lo[NO], q_hi[NO];
+#pragma unroll
+    for (int k = 0; k < NO; ++k) q_max[k] = q_lo[k] = q_hi[k] = __uint_as_float(kCanonNaN);
+    // PSIG 1: per-lane product state lives in shared memory: [word][field of the lane][thread]
     if constexpr (PROD) {
         float x = 0.f, y = 0.f;
         if (owner) {
@@ -665,11 +716,14 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
         }
         ColumnState st;
         st.init(p.prod, x, y);
-        st.store_words(p.prod, sm_state, 0, 1);
-        st.store_levels(p.prod, sm_state, 1);
+#pragma unroll
+        for (int k = 0; k < NO; ++k) st.store_words(p.prod, sm_state, k, NO);
+        st.store_levels(p.prod, sm_state, NO);
     }
 
-    float* const out = owner ? p.grid_out[gl] : nullptr;
+    float* out[NO];
+#pragma unroll
+    for (int k = 0; k < NO; ++k) out[k] = !QS && owner && gl + k * W < F ? p.grid_out[gl + k * W] : nullptr;
     // Row bounds run two levels ahead of the sums, so that the L2 prefetch of level z+1 (issued while level z is
     // summed) never waits for the bounds load it depends on.
     // IL: (bs, be) are the slice's two quad_ptr words, identical in all lanes of the warp
@@ -716,9 +770,11 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
         const uint32_t il_p0 = s >> 1, il_m = (e >> 1) - il_p0;
         const bool il_hv = s & 1u;
         const uint32_t len = IL ? il_m + (il_hv ? 1u : 0u) : e - s;
-        float a = 0.f, b = 0.f;
+        float a[NO], b[NO];
+#pragma unroll
+        for (int k = 0; k < NO; ++k) a[k] = b[k] = 0.f;
         // warps whose four rows are all empty (outside the radar range, above the highest sweep) skip the sums
-        if (__any_sync(kFull, len != 0)) {
+        if (IL ? len != 0 : __any_sync(kFull, len != 0)) {     // IL: len is the same in all lanes
             float swv[F], sw[F];
 #pragma unroll
             for (int f = 0; f < F; ++f) { swv[f] = 0.f; sw[f] = 0.f; }
@@ -735,7 +791,7 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
             if constexpr (W < 32) {
                 // Rows far longer than the group is wide (the voxels next to the radar see the first gates
                 // of every ray) are summed by the whole warp, then handed back to the owning group.
-                unsigned heavy = __any_sync(kFull, heavy_mine) ? __ballot_sync(kFull, heavy_mine && gl == 0) : 0u;
+                unsigned heavy = (IL ? il_hv : __any_sync(kFull, heavy_mine)) ? __ballot_sync(kFull, heavy_mine && gl == 0) : 0u;
                 while (heavy) {
                     const int src = __ffs(heavy) - 1;
                     heavy &= heavy - 1;
@@ -859,7 +915,9 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
                         sw[f] += __shfl_xor_sync(kFull, sw[f], off);
                     }
                 }
-                group8_reduce_scatter<F>(swv, sw, gl & 7, a, b);
+                group8_reduce_scatter<F>(swv, sw, gl & 7, a[0], b[0]);
+            } else if constexpr (RG_TREDUCE && W == 4) {
+                group4_reduce_scatter<F, NO>(swv, sw, gl, a, b);
             } else {
                 // butterfly inside the group: afterwards every lane of the group holds the row sums
 #pragma unroll
@@ -872,31 +930,56 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
                 }
 #pragma unroll
                 for (int f = 0; f < F; ++f)
-                    if (gl == f) { a = swv[f]; b = sw[f]; }
+                    if (gl + (f / W) * W == f) { a[f / W] = swv[f]; b[f / W] = sw[f]; }
             }
         }
 
-        if (owner) {
-            const float v = b > 0.f ? fast_div(a, b) : p.fill;             // interpolate.py:99-102
-            if (out != nullptr) __stcs(out + row, v);
-            if constexpr (PROD) {
-                ColumnState::update_words(p.prod, sm_state, 0, 1, p.z_begin + lz, v);
-            }
-            if constexpr (PSIG == 2) {
-                const int z = p.z_begin + lz;
-                if ((unsigned)(z - p.prod.cmax_z0) < p.prod.cmax_w && !isnan(v)) q_max = isnan(q_max) ? v : fmaxf(q_max, v);
-                if (z == p.prod.slices[0].z_lo) q_lo = v;
-                if (z == p.prod.slices[0].z_hi) q_hi = v;
+#pragma unroll
+        for (int k = 0; k < NO; ++k) {
+            if (owner && gl + k * W < F) {
+                const float v = b[k] > 0.f ? fast_div(a[k], b[k]) : p.fill;        // interpolate.py:99-102
+                // QS: pointer from the parameter bank, no register held across levels
+                float* const dst = QS ? p.grid_out[gl + k * W] : out[k];
+                if (dst != nullptr) __stcs(dst + row, v);
+                if constexpr (PROD) {
+                    ColumnState::update_words(p.prod, sm_state, k, NO, p.z_begin + lz, v);
+                }
+                if constexpr (PSIG == 2) {
+                    const int z = p.z_begin + lz;
+                    if constexpr (QS) {
+                        float* const qs = q_state + k * kApplyThreads + threadIdx.x;
+                        if ((unsigned)(z - p.prod.cmax_z0) < p.prod.cmax_w && !isnan(v)) {
+                            const float c = qs[0];
+                            qs[0] = isnan(c) ? v : fmaxf(c, v);
+                        }
+                        if (z == p.prod.slices[0].z_lo) qs[NO * kApplyThreads] = v;
+                        if (z == p.prod.slices[0].z_hi) qs[2 * NO * kApplyThreads] = v;
+                    } else {
+                        if ((unsigned)(z - p.prod.cmax_z0) < p.prod.cmax_w && !isnan(v)) q_max[k] = isnan(q_max[k]) ? v : fmaxf(q_max[k], v);
+                        if (z == p.prod.slices[0].z_lo) q_lo[k] = v;
+                        if (z == p.prod.slices[0].z_hi) q_hi[k] = v;
+                    }
+                }
             }
         }
     }
     if constexpr (PSIG == 2) {
-        if (owner) {
-            ColumnState st;
-            st.cmax = q_max;
-            st.s_lo[0] = q_lo;
-            st.s_hi[0] = q_hi;
-            st.write(p.prod, gl, col, p.ncol, 0.f, 0.f);       // only cmax and the LEVEL slice are on: x, y unused
+#pragma unroll
+        for (int k = 0; k < NO; ++k) {
+            if (owner && gl + k * W < F) {
+                ColumnState st;
+                if constexpr (QS) {
+                    const float* const qs = q_state + k * kApplyThreads + threadIdx.x;
+                    st.cmax = qs[0];
+                    st.s_lo[0] = qs[NO * kApplyThreads];
+                    st.s_hi[0] = qs[2 * NO * kApplyThreads];
+                } else {
+                    st.cmax = q_max[k];
+                    st.s_lo[0] = q_lo[k];
+                    st.s_hi[0] = q_hi[k];
+                }
+                st.write(p.prod, gl + k * W, col, p.ncol, 0.f, 0.f);   // only cmax and the LEVEL slice are on: x, y unused
+            }
         }
     }
 
@@ -904,10 +987,15 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
         if (owner) {
             const float x = __ldg(p.prod.x_ax + (int)(col % p.nx));
             const float y = __ldg(p.prod.y_ax + (int)(col / p.nx));
-            ColumnState st;
-            st.load_words(p.prod, sm_state, 0, 1);
-            st.load_levels(p.prod, sm_state, 1);
-            st.write(p.prod, gl, col, p.ncol, x, y);
+#pragma unroll
+            for (int k = 0; k < NO; ++k) {
+                if (gl + k * W < F) {
+                    ColumnState st;
+                    st.load_words(p.prod, sm_state, k, NO);
+                    st.load_levels(p.prod, sm_state, NO);
+                    st.write(p.prod, gl + k * W, col, p.ncol, x, y);
+                }
+            }
         }
     }
 }
@@ -1173,29 +1261,29 @@ static void launch_columns(Context* ctx, const ApplyParams& p)
 #else
     const unsigned blocks = (unsigned)((p.ncol + cols_per_cta - 1) / cols_per_cta);
 #endif
-    const size_t smem = (size_t)(p.prod.n_state_words + RG_MAX_SLICES) * kApplyThreads * sizeof(float);
+    constexpr int NO = W < F ? 2 : 1;                             // fields per owner lane, as in the kernel
+    const size_t smem = (size_t)(p.prod.n_state_words * NO + RG_MAX_SLICES) * kApplyThreads * sizeof(float);
     const ProductParams& pp = p.prod;
     const bool simple = pp.any && !pp.cmin_on && !pp.cmean_on && pp.n_slices <= 1 &&
                         (pp.n_slices == 0 || pp.slices[0].kind == RG_PROD_LEVEL) && ctx->apply_variant != 3;
+    const size_t smem2 = RG_QSMEM && NO > 1 ? (size_t)3 * NO * kApplyThreads * sizeof(float) : 0;   // PSIG 2 state (QS)
     if (p.quads != nullptr) {
 #if RG_TILE2D
         if (!pp.any) apply_columns_kernel<F, W, 0, true><<<blocks, kApplyThreads, 0, ctx->stream>>>(p);
-        else if (simple) apply_columns_kernel<F, W, 2, true><<<blocks, kApplyThreads, 0, ctx->stream>>>(p);
+        else if (simple) apply_columns_kernel<F, W, 2, true><<<blocks, kApplyThreads, smem2, ctx->stream>>>(p);
         else apply_columns_kernel<F, W, 1, true><<<blocks, kApplyThreads, smem, ctx->stream>>>(p);
         return;
 #endif
     }
     if (!pp.any) apply_columns_kernel<F, W, 0, false><<<blocks, kApplyThreads, 0, ctx->stream>>>(p);
-    else if (simple) apply_columns_kernel<F, W, 2, false><<<blocks, kApplyThreads, 0, ctx->stream>>>(p);
+    else if (simple) apply_columns_kernel<F, W, 2, false><<<blocks, kApplyThreads, smem2, ctx->stream>>>(p);
     else apply_columns_kernel<F, W, 1, false><<<blocks, kApplyThreads, smem, ctx->stream>>>(p);
 }
 
 template <int F>
 static int launch_columns_w(Context* ctx, const ApplyParams& p, int W)
 {
-    if constexpr (F <= 4) {
-        if (W == 4) { launch_columns<F, 4>(ctx, p); return RG_OK; }
-    }
+    if (W == 4) { launch_columns<F, 4>(ctx, p); return RG_OK; }
     if (W <= 8) launch_columns<F, 8>(ctx, p);
     else if (W == 16) launch_columns<F, 16>(ctx, p);
     else launch_columns<F, 32>(ctx, p);
@@ -1217,16 +1305,31 @@ static int launch_sell(Context* ctx, const ApplyParams& p)
     return RG_OK;
 }
 
-static int pick_group_width(const Context* ctx, const Geometry* g, int n_fields)
+// Pairs from the warp-slice copy?  It pays when the kernel is bound by instruction issue and the L1 data pipe (several
+// fields per pair); a single-field pass over a large table is HBM-bound and better off without the padding.
+static bool use_slices(const Context* ctx, int n_fields)
+{
+#if RG_TILE2D && RG_HEADBATCH == 2
+    if (ctx->apply_variant == 4) return true;
+    if (ctx->apply_variant == 1) return false;
+    return n_fields >= 2;
+#else
+    return false;
+#endif
+}
+
+static int pick_group_width(const Context* ctx, const Geometry* g, int n_fields, bool slices)
 {
     int W = (int)ctx->group_width;
     if (W == 0) {
         const int64_t nonempty = g->info.n_rows - g->info.n_empty_rows;
         const double avg = nonempty > 0 ? (double)g->info.n_pairs / (double)nonempty : 0.0;
-        W = avg < 24.0 ? 4 : avg < 160.0 ? 8 : avg < 600.0 ? 16 : 32;     // measured: cfg1 (avg 16) W=4, cfg3 (avg 40) W=8
+        // measured on B200: CSR copy: cfg1 (avg 16) W=4, cfg3 (avg 40) W=8; slice copy: cfg3 W=4 (0.71 vs 0.81 ms)
+        if (slices) W = avg < 96.0 ? 4 : avg < 320.0 ? 8 : avg < 1200.0 ? 16 : 32;
+        else W = avg < 24.0 ? 4 : avg < 160.0 ? 8 : avg < 600.0 ? 16 : 32;
+        if (!slices && W < 8 && n_fields > 4) W = 8;
     }
     if (W != 4 && W != 8 && W != 16 && W != 32) W = 8;
-    if (W < 8 && n_fields > 4) W = 8;
     return W;
 }
 
@@ -1265,13 +1368,14 @@ int launch_apply(Context* ctx, const Geometry* g, const ApplyParams& p, bool ref
         RG_CUDA(cudaGetLastError());
         return RG_OK;
     }
-    const int W = pick_group_width(ctx, g, p.n_fields);
+    const bool slices = use_slices(ctx, p.n_fields);
+    const int W = pick_group_width(ctx, g, p.n_fields, slices);
     ApplyParams q = p;
     q.quads = nullptr;
     q.quad_ptr = nullptr;
     q.quads_x = 0;
 #if RG_TILE2D && RG_HEADBATCH == 2
-    if (ctx->apply_variant == 4) {                      // pairs from the warp-slice copy (built on first use)
+    if (slices) {                                       // pairs from the warp-slice copy (built on first use)
         const Geometry::QuadCopy* qc = nullptr;
         RG_TRY(ensure_quads(ctx, const_cast<Geometry*>(g), W, &qc));
         q.quads = qc->quads;

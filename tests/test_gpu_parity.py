@@ -213,7 +213,18 @@ def test_zslab_shards_concatenate_and_colmax_reduces():
     names = list(fields)
     data = [np.ma.getdata(fields[n]) for n in names]
     masks = [np.ma.getmaskarray(fields[n]) for n in names]
-    full = rg.grid_fields(build(spec, gates, "barnes2", 0), data, masks=masks, products=[rg.ColumnMax(), rg.ColumnMin()])
+    whole = build(spec, gates, "barnes2", 0)
+    # bit-for-bit equality needs the same summation order, i.e. the same group width, for the slabs and the whole grid
+    # (left to itself the library picks it from each table's mean row length)
+    whole.ctx.set_option("group_width", 8)
+    try:
+        _zslab_checks(spec, gates, names, data, masks, whole, D, torch)
+    finally:
+        whole.ctx.set_option("group_width", 0)
+
+
+def _zslab_checks(spec, gates, names, data, masks, whole, D, torch):
+    full = rg.grid_fields(whole, data, masks=masks, products=[rg.ColumnMax(), rg.ColumnMin()])
     parts, cmax, cmin = [], None, None
     for z0, z1 in D.zslab_ranges(spec.grid_shape[0], 3):
         slab = build(spec, gates, "barnes2", 0, z_range=(z0, z1))

@@ -4,7 +4,7 @@ set -u
 mkdir -p gpurun_out
 echo "== smoke"; timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2
 echo "== pytest gpu"; timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider 2>&1 | tail -8
-for av in 2 3; do echo "== pytest parity, apply_variant=$av"; RG_APPLY_VARIANT_TEST=$av timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_known_answers.py -m gpu -q -p no:cacheprovider 2>&1 | tail -2; done
+for av in 1 2 3; do echo "== pytest parity, apply_variant=$av"; RG_APPLY_VARIANT_TEST=$av timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_known_answers.py -m gpu -q -p no:cacheprovider 2>&1 | tail -2; done
 echo "== bench"; timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"; python -c "
 import json; d=json.load(open('gpurun_out/bench.json'))
 print({k: d[k] for k in ('value','ms_per_step','n_gpus','gpu_launches')}); print(d['roofline']); print(d['e2e']); print(d['clocks']); print(d.get('cpu_baseline'))"; tail -3 gpurun_out/bench.err
