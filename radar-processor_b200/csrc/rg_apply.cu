@@ -427,10 +427,13 @@ int launch_products(Context* ctx, const rg_grid_spec& grid, int n_fields, const 
 __device__ __forceinline__ float fast_div(float a, float b)
 {
 #if RG_FASTDIV && !defined(RG_EMU)
-    // b is a positive, finite sum of weights here; one Newton step on the hardware reciprocal
+    // b is a positive, finite sum of weights here: hardware reciprocal (1 ulp), then one residual correction of
+    // the quotient -- within 1 ulp of the IEEE quotient, far inside the 1e-5 relative bar of the fast path
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+#if RG_FASTDIV == 2
     r = fmaf(fmaf(-b, r, 1.0f), r, r);
+#endif
     const float q = a * r;
     return fmaf(fmaf(-b, q, a), r, q);
 #else
@@ -731,23 +734,30 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
     const uint32_t* __restrict__ quad_ptr = p.quad_ptr;
     const int qx = cx / (32 / W);
     const bool slice_ok = cy < p.ny && qx < p.quads_x;
-    auto bounds = [&](int lz, uint32_t& bs, uint32_t& be) {
+    // The bounds words of consecutive levels are a fixed stride apart: walk a pointer instead of re-deriving the index.
+    const uint32_t* bp;
+    size_t bstride;
+    bool b_ok;
+    if constexpr (IL) {
+        bp = quad_ptr + ((size_t)p.lz_first * (size_t)p.ny + (size_t)cy) * (size_t)p.quads_x + (size_t)qx;
+        bstride = (size_t)p.ny * (size_t)p.quads_x;
+        b_ok = slice_ok;
+    } else {
+        bp = indptr + (size_t)p.lz_first * (size_t)p.ncol + (size_t)col;
+        bstride = (size_t)p.ncol;
+        b_ok = col_ok;
+    }
+    auto bounds = [&](const uint32_t* ptr, int lz, uint32_t& bs, uint32_t& be) {
         bs = be = 0;
-        if constexpr (IL) {
-            if (slice_ok && lz < p.lz_last) {
-                const size_t q = ((size_t)lz * (size_t)p.ny + (size_t)cy) * (size_t)p.quads_x + (size_t)qx;
-                bs = __ldg(quad_ptr + q);
-                be = __ldg(quad_ptr + q + 1);
-            }
-        } else if (col_ok && lz < p.lz_last) {
-            const size_t r = (size_t)lz * (size_t)p.ncol + (size_t)col;
-            bs = __ldg(indptr + r);
-            be = __ldg(indptr + r + 1);
+        if (b_ok && lz < p.lz_last) {
+            bs = __ldg(ptr);
+            be = __ldg(ptr + 1);
         }
     };
     uint32_t s_next, e_next, s_next2, e_next2;
-    bounds(p.lz_first, s_next, e_next);
-    bounds(p.lz_first + 1, s_next2, e_next2);
+    bounds(bp, p.lz_first, s_next, e_next);
+    bounds(bp + bstride, p.lz_first + 1, s_next2, e_next2);
+    bp += 2 * bstride;                                         // bounds of the level two ahead of the loop variable
 
     size_t row = (size_t)p.lz_first * (size_t)p.ncol + (size_t)col - (size_t)p.ncol;
     for (int lz = p.lz_first; lz < p.lz_last; ++lz) {
@@ -755,7 +765,8 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
         row += (size_t)p.ncol;
         s_next = s_next2;
         e_next = e_next2;
-        bounds(lz + 2, s_next2, e_next2);
+        bounds(bp, lz + 2, s_next2, e_next2);
+        bp += IL ? (size_t)p.ny * (size_t)p.quads_x : (size_t)p.ncol;
 #if RG_PREFETCH > 0
         if constexpr (IL) {   // level z+1's slots are contiguous: one 128-byte line per lane
             const uint32_t l0 = (s_next >> 1) * 2u + (uint32_t)lane;
@@ -859,6 +870,15 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
                     }
                 };
                 static_assert(H == 7 || H == 5 || H == 3, "head sizes are written out below");
+                if constexpr (IL) {
+                    // the slot count is warp-uniform: full batches of H first, then ONE exactly sized batch, so that
+                    // long rows never run slots that only hold padding
+                    while (m > (uint32_t)H) {
+                        head(std::integral_constant<int, H>{});
+                        il_base += H * 32;
+                        m -= (uint32_t)H;
+                    }
+                }
                 switch (m < (uint32_t)H ? m : (uint32_t)H) {
                     case 0: break;
                     case 1: head(std::integral_constant<int, 1>{}); break;
@@ -869,9 +889,8 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
                     case 6: if constexpr (H >= 6) head(std::integral_constant<int, 6>{}); break;
                     default: if constexpr (H >= 7) head(std::integral_constant<int, 7>{}); break;
                 }
-                if (m > (uint32_t)H) {
-                    if constexpr (IL) gather_run<F>(il_base + H * 32, rec, 0u, (m - (uint32_t)H) * 32u, 32u, swv, sw);
-                    else gather_run<F>(pairs, rec, min(s + gl + H * W, lim), lim, W, swv, sw);
+                if constexpr (!IL) {
+                    if (m > (uint32_t)H) gather_run<F>(pairs, rec, min(s + gl + H * W, lim), lim, W, swv, sw);
                 }
             }
 #elif RG_HEADBATCH
@@ -952,8 +971,10 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
                             const float c = qs[0];
                             qs[0] = isnan(c) ? v : fmaxf(c, v);
                         }
-                        if (z == p.prod.slices[0].z_lo) qs[NO * kApplyThreads] = v;
-                        if (z == p.prod.slices[0].z_hi) qs[2 * NO * kApplyThreads] = v;
+                        if (z == p.prod.slices[0].z_lo || z == p.prod.slices[0].z_hi) {     // uniform: two levels of the column
+                            if (z == p.prod.slices[0].z_lo) qs[NO * kApplyThreads] = v;
+                            if (z == p.prod.slices[0].z_hi) qs[2 * NO * kApplyThreads] = v;
+                        }
                     } else {
                         if ((unsigned)(z - p.prod.cmax_z0) < p.prod.cmax_w && !isnan(v)) q_max[k] = isnan(q_max[k]) ? v : fmaxf(q_max[k], v);
                         if (z == p.prod.slices[0].z_lo) q_lo[k] = v;
