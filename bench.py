@@ -240,9 +240,11 @@ def run_b200(args):
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
         # the same volume through one synchronous call (no overlap), for the record
-        t0 = time.perf_counter()
-        rg.grid_fields(dev, ctx=ctx, **slots[0])
-        e2e_single_ms = (time.perf_counter() - t0) * 1e3
+        e2e_single_ms = float("inf")
+        for _ in range(3):                                                  # best of three: the first one pays host-side one-offs
+            t0 = time.perf_counter()
+            rg.grid_fields(dev, ctx=ctx, **slots[0])
+            e2e_single_ms = min(e2e_single_ms, (time.perf_counter() - t0) * 1e3)
         if world > 1:
             t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

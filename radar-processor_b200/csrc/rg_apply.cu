@@ -1399,9 +1399,11 @@ int launch_apply(Context* ctx, const Geometry* g, const ApplyParams& p, bool ref
     if (slices) {                                       // pairs from the warp-slice copy (built on first use)
         const Geometry::QuadCopy* qc = nullptr;
         RG_TRY(ensure_quads(ctx, const_cast<Geometry*>(g), W, &qc));
-        q.quads = qc->quads;
-        q.quad_ptr = qc->ptr;
-        q.quads_x = qc->quads_x;
+        if (qc != nullptr) {                            // nullptr: no room for the copy, read the CSR copy
+            q.quads = qc->quads;
+            q.quad_ptr = qc->ptr;
+            q.quads_x = qc->quads_x;
+        }
     }
 #endif
     timer_begin(ctx, kTimerApply);

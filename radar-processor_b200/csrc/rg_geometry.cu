@@ -616,6 +616,7 @@ int ensure_quads(Context* ctx, Geometry* g, int W, const Geometry::QuadCopy** ou
     Geometry::QuadCopy& qc = g->quad[slot];
     *out = &qc;
     if (qc.ptr != nullptr) return RG_OK;
+    if (qc.n_slots < 0) { *out = nullptr; return RG_OK; }      // did not fit earlier
     const int R = 32 / W, nx = g->grid.nx, ny = g->grid.ny;
     const int quads_x = (nx + R - 1) / R;
     const int64_t n_slices = (int64_t)g->n_levels * ny * quads_x;
@@ -639,6 +640,16 @@ int ensure_quads(Context* ctx, Geometry* g, int W, const Geometry::QuadCopy** ou
     uint64_t total = 0;
     RG_TRY(exclusive_scan_u32(ctx, counts.p, offs.p, n_slices, tmp.p, &total));
     if (total >= (1ull << 31)) return fail(RG_ERR_UNSUPPORTED, "warp-slice copy of the table exceeds 2^31 slots; use more z-slabs");
+    // The copy is an accelerator, not a requirement: when it does not fit next to the table (a z-slab sized to fill
+    // the GPU), the kernel keeps reading the CSR copy.
+    size_t free_b = 0, total_b = 0;
+    RG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t need_b = (size_t)total * 32 * sizeof(uint2);
+    if (need_b + (size_t)(1ull << 30) > free_b) {
+        qc.n_slots = -1;                                       // remembered: do not try again for this table
+        *out = nullptr;
+        return RG_OK;
+    }
     DevBuf<uint2> quads;
     RG_CUDA(quads.alloc((size_t)total * 32));
     if (n_slices > 0) {
