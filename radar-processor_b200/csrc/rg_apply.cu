@@ -510,7 +510,7 @@ __device__ __forceinline__ void group4_reduce_scatter(const float (&swv)[F], con
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int lo = j < 2 ? j : j + 2, hi = lo + 2;       // (0,2) (1,3) (4,6) (5,7)
-            if (lo < F) {
+            if (lo < F && !(F == 5 && lo == 4)) {
                 t_wv[j] = (up ? u_wv[hi] : u_wv[lo]) + __shfl_xor_sync(kFull, up ? u_wv[lo] : u_wv[hi], 2);
                 t_w[j] = (up ? u_w[hi] : u_w[lo]) + __shfl_xor_sync(kFull, up ? u_w[lo] : u_w[hi], 2);
             } else {
@@ -522,7 +522,14 @@ __device__ __forceinline__ void group4_reduce_scatter(const float (&swv)[F], con
     const bool up = gl & 1;
     a[0] = (up ? t_wv[1] : t_wv[0]) + __shfl_xor_sync(kFull, up ? t_wv[0] : t_wv[1], 1);
     b[0] = (up ? t_w[1] : t_w[0]) + __shfl_xor_sync(kFull, up ? t_w[0] : t_w[1], 1);
-    if constexpr (NO > 1) {
+    if constexpr (F == 5) {
+        // a single unit in the upper half: a plain butterfly (no selects) is cheaper than scattering it
+        float x = u_wv[4], y = u_w[4];
+        x += __shfl_xor_sync(kFull, x, 2);
+        y += __shfl_xor_sync(kFull, y, 2);
+        a[1] = x + __shfl_xor_sync(kFull, x, 1);
+        b[1] = y + __shfl_xor_sync(kFull, y, 1);
+    } else if constexpr (NO > 1) {
         a[1] = (up ? t_wv[3] : t_wv[2]) + __shfl_xor_sync(kFull, up ? t_wv[2] : t_wv[3], 1);
         b[1] = (up ? t_w[3] : t_w[2]) + __shfl_xor_sync(kFull, up ? t_w[2] : t_w[3], 1);
     }
@@ -953,36 +960,45 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
             }
         }
 
+        // EMPTY: the whole slice has no pairs at this level (above the highest sweep, beyond the last gate): every
+        // output is the fill value; with a NaN fill the running maximum is not touched either.
+        auto finish = [&](auto empty_tag) {
+            constexpr bool EMPTY = decltype(empty_tag)::value;
 #pragma unroll
-        for (int k = 0; k < NO; ++k) {
-            if (owner && gl + k * W < F) {
-                const float v = b[k] > 0.f ? fast_div(a[k], b[k]) : p.fill;        // interpolate.py:99-102
-                // QS: pointer from the parameter bank, no register held across levels
-                float* const dst = QS ? p.grid_out[gl + k * W] : out[k];
-                if (dst != nullptr) __stcs(dst + row, v);
-                if constexpr (PROD) {
-                    ColumnState::update_words(p.prod, sm_state, k, NO, p.z_begin + lz, v);
-                }
-                if constexpr (PSIG == 2) {
-                    const int z = p.z_begin + lz;
-                    if constexpr (QS) {
-                        float* const qs = q_state + k * kApplyThreads + threadIdx.x;
-                        if ((unsigned)(z - p.prod.cmax_z0) < p.prod.cmax_w && !isnan(v)) {
-                            const float c = qs[0];
-                            qs[0] = isnan(c) ? v : fmaxf(c, v);
+            for (int k = 0; k < NO; ++k) {
+                if (owner && gl + k * W < F) {
+                    const float v = !EMPTY && b[k] > 0.f ? fast_div(a[k], b[k]) : p.fill;      // interpolate.py:99-102
+                    // QS: pointer from the parameter bank, no register held across levels
+                    float* const dst = QS ? p.grid_out[gl + k * W] : out[k];
+                    if (dst != nullptr) __stcs(dst + row, v);
+                    if constexpr (PROD) {
+                        ColumnState::update_words(p.prod, sm_state, k, NO, p.z_begin + lz, v);
+                    }
+                    if constexpr (PSIG == 2) {
+                        const int z = p.z_begin + lz;
+                        if constexpr (QS) {
+                            float* const qs = q_state + k * kApplyThreads + threadIdx.x;
+                            if (!EMPTY || !isnan(p.fill)) {
+                                if ((unsigned)(z - p.prod.cmax_z0) < p.prod.cmax_w && !isnan(v)) {
+                                    const float c = qs[0];
+                                    qs[0] = isnan(c) ? v : fmaxf(c, v);
+                                }
+                            }
+                            if (z == p.prod.slices[0].z_lo || z == p.prod.slices[0].z_hi) {     // uniform: two levels of the column
+                                if (z == p.prod.slices[0].z_lo) qs[NO * kApplyThreads] = v;
+                                if (z == p.prod.slices[0].z_hi) qs[2 * NO * kApplyThreads] = v;
+                            }
+                        } else {
+                            if ((unsigned)(z - p.prod.cmax_z0) < p.prod.cmax_w && !isnan(v)) q_max[k] = isnan(q_max[k]) ? v : fmaxf(q_max[k], v);
+                            if (z == p.prod.slices[0].z_lo) q_lo[k] = v;
+                            if (z == p.prod.slices[0].z_hi) q_hi[k] = v;
                         }
-                        if (z == p.prod.slices[0].z_lo || z == p.prod.slices[0].z_hi) {     // uniform: two levels of the column
-                            if (z == p.prod.slices[0].z_lo) qs[NO * kApplyThreads] = v;
-                            if (z == p.prod.slices[0].z_hi) qs[2 * NO * kApplyThreads] = v;
-                        }
-                    } else {
-                        if ((unsigned)(z - p.prod.cmax_z0) < p.prod.cmax_w && !isnan(v)) q_max[k] = isnan(q_max[k]) ? v : fmaxf(q_max[k], v);
-                        if (z == p.prod.slices[0].z_lo) q_lo[k] = v;
-                        if (z == p.prod.slices[0].z_hi) q_hi[k] = v;
                     }
                 }
             }
-        }
+        };
+        if (IL && len == 0) finish(std::true_type{});
+        else finish(std::false_type{});
     }
     if constexpr (PSIG == 2) {
 #pragma unroll

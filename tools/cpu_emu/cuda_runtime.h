@@ -182,6 +182,7 @@ typedef void* cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
 enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 template <typename K> inline cudaError_t cudaFuncSetAttribute(K, int, int) { return cudaSuccess; }
+inline cudaError_t cudaMemGetInfo(size_t* free_b, size_t* total_b) { *free_b = *total_b = (size_t)64 << 30; return cudaSuccess; }
 enum { cudaStreamNonBlocking = 1, cudaHostAllocDefault = 0, cudaDevAttrMultiProcessorCount = 16 };
 inline const char* cudaGetErrorString(cudaError_t) { return "emulated CUDA error"; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
