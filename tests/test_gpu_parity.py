@@ -118,6 +118,33 @@ def test_fast_apply_within_tolerance(spec_name, weighting, alt, own_table):
     dev.ctx.set_option("group_width", 0)
 
 
+@pytest.mark.parametrize("spec_name", ["tiny", "small"])
+def test_slice_copy_and_csr_copy_sum_in_the_same_order(spec_name):
+    """The warp-slice copy only changes where a lane's pairs are read from, not which pairs it takes or in which order:
+    at equal group width the two table layouts must agree bit for bit, grids and fused products alike."""
+    spec, radar, gates, fields, g = golden_case(spec_name)
+    dev = build(spec, gates, "barnes2", 0)
+    names = list(fields)
+    data = [np.ma.getdata(fields[n]) for n in names]
+    masks = [np.ma.getmaskarray(fields[n]) for n in names]
+    reqs = [rg.ColumnMax(), rg.CAPPI(1234.5)]
+    try:
+        for width in (4, 8, 16, 32):
+            dev.ctx.set_option("group_width", width)
+            for nf in (1, 2, len(names)):
+                out = {}
+                for variant in (1, 4):
+                    dev.ctx.set_option("apply_variant", variant)
+                    out[variant] = rg.grid_fields(dev, data[:nf], masks=masks[:nf], products=reqs)
+                for f in range(nf):
+                    assert_same(out[1]["grids"][f], out[4]["grids"][f], f"W={width} F={nf} grid {f}")
+                for a, b in zip(out[1]["products"], out[4]["products"]):
+                    assert_same(a, b, f"W={width} F={nf} products")
+    finally:
+        dev.ctx.set_option("group_width", 0)
+        dev.ctx.set_option("apply_variant", 0)
+
+
 def test_fused_qc_rule_equals_host_mask_and_masked_invalid_on_device():
     spec, radar, gates, fields, g = golden_case("small")
     dev = build(spec, gates, "barnes2", 0)
