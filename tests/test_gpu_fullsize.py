@@ -98,11 +98,14 @@ def test_reference_order_and_fast_kernels_agree(case):
     exact = rg.grid_fields(dev, [data], masks=[mask], reference_order=True)["grids"][0]
     np.testing.assert_array_equal(np.isnan(fast), np.isnan(exact))
     np.testing.assert_allclose(fast, exact, rtol=1e-5, atol=1e-4, equal_nan=True)
-    for variant in (2, 3):                       # the A/B kernels give the same answer
-        dev.ctx.set_option("apply_variant", variant)
-        alt = rg.grid_fields(dev, [data], masks=[mask], products=[rg.ColumnMax()])
-        np.testing.assert_allclose(alt["grids"][0], exact, rtol=1e-5, atol=1e-4, equal_nan=True)
-    dev.ctx.set_option("apply_variant", 0)
+    import os
+    try:
+        for variant in (1, 2, 3, 4):             # the A/B kernels and both table layouts give the same answer
+            dev.ctx.set_option("apply_variant", variant)
+            alt = rg.grid_fields(dev, [data], masks=[mask], products=[rg.ColumnMax()])
+            np.testing.assert_allclose(alt["grids"][0], exact, rtol=1e-5, atol=1e-4, equal_nan=True)
+    finally:
+        dev.ctx.set_option("apply_variant", int(os.environ.get("RG_APPLY_VARIANT_TEST") or 0))
 
 
 def test_full_size_bit_exact_against_the_oracle_on_the_same_table(case):
