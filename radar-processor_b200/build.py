@@ -56,13 +56,30 @@ def build(force=False, variant="", extra_flags=(), verbose=False):
         if os.path.exists(out):
             return out          # GPU box without the sources' toolchain: use the shipped binary
         raise RuntimeError("nvcc not found and no prebuilt libradargrid_b200.so")
-    cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + SRC
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed")
-    if verbose:
-        sys.stderr.write(res.stderr)
+    # one nvcc per source file, in parallel (rg_apply.cu alone instantiates ~190 kernels), then one link step
+    import tempfile
+    from concurrent.futures import ThreadPoolExecutor
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + list(extra_flags) + (["-Xptxas", "-v"] if verbose else [])
+    with tempfile.TemporaryDirectory(prefix="rg_build_") as tmp:
+        objs = [os.path.join(tmp, os.path.basename(f)[:-3] + ".o") for f in SRC]
+
+        def compile_one(job):
+            src, obj = job
+            return subprocess.run([nvcc] + flags + ["-c", src, "-o", obj], capture_output=True, text=True)
+
+        with ThreadPoolExecutor(max_workers=len(SRC)) as pool:
+            results = list(pool.map(compile_one, zip(SRC, objs)))
+        for res in results:
+            if res.returncode != 0:
+                sys.stderr.write(res.stdout + res.stderr)
+                raise RuntimeError("nvcc failed")
+            if verbose:
+                sys.stderr.write(res.stderr)
+        res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs,
+                             capture_output=True, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError("nvcc link failed")
     with open(stamp, "w") as fh:
         fh.write(digest)
     return out
