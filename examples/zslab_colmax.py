@@ -29,6 +29,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--spec", default="cfg5")
     ap.add_argument("--slabs", type=int, default=8)
+    ap.add_argument("--cappi", type=float, default=None, metavar="ALT_M",
+                    help="also a CAPPI at this altitude: level picks out of the same pass, one all-reduce(sum)")
     ap.add_argument("--check", action="store_true", help="also build the whole grid in one piece and compare (small specs)")
     args = ap.parse_args()
 
@@ -57,6 +59,8 @@ def main():
     slabs = D.zslab_ranges(nz, args.slabs)
     mine = [slabs[i] for i in D.shard_volumes(len(slabs), world, rank)]
     partial = torch.full((1, ny, nx), float("nan"), device="cuda")
+    cappi_req = None if args.cappi is None else rg.CAPPI(args.cappi)
+    cappi_acc, cappi_owned = None, []
     log = []
     todo = list(mine)
     while todo:
@@ -75,8 +79,18 @@ def main():
             continue
         t_build = time.perf_counter() - t0
         t0 = time.perf_counter()
-        res = rg.grid_fields(geom, [dfield], mask_invalid=True, want_grid=False, products=[rg.ColumnMax()], ctx=ctx)
+        levels = []
+        if cappi_req is not None:
+            plan = D.cappi_zslab_terms(cappi_req, spec.grid_shape, spec.grid_limits, (z0, z1))
+            levels = [] if plan is None else [z for z, _ in plan[0]]
+        res = rg.grid_fields(geom, [dfield], mask_invalid=True, want_grid=False,
+                             products=[rg.ColumnMax()] + [rg.LevelPick(z) for z in levels], ctx=ctx)
         ctx.synchronize()
+        if levels:
+            part = D.cappi_zslab_partial(cappi_req, spec.grid_shape, spec.grid_limits, (z0, z1),
+                                         lambda lv: res["products"][1:], partial)
+            cappi_acc = part if cappi_acc is None else cappi_acc + part
+            cappi_owned += levels
         t_apply = time.perf_counter() - t0
         plane = res["products"][0]
         partial = torch.fmax(partial, plane)                 # fmax ignores NaN, as np.nanmax does
@@ -86,15 +100,35 @@ def main():
                     "table_GB": round(info["device_bytes"] / 1e9, 2)})
         geom.close()
     colmax = D.allreduce_nanmax(partial)                      # one NCCL all-reduce(max) across the ranks
+    cappi = None
+    if cappi_req is not None:
+        plan = D.cappi_zslab_terms(cappi_req, spec.grid_shape, spec.grid_limits, (0, nz))
+        if plan is None:
+            cappi = torch.full_like(partial, float("nan"))
+        else:
+            if cappi_acc is None:                             # this rank owns neither level: the neutral element
+                cappi_acc = torch.full_like(partial, -0.0, dtype=torch.float32 if plan[1] == np.float32 else torch.float64)
+            if world > 1:
+                dist.all_reduce(cappi_acc, op=dist.ReduceOp.SUM)      # the two-party sum of SURVEY 8e
+            cappi = cappi_acc.to(torch.float32)
     torch.cuda.synchronize()
 
     out = {"spec": spec.name, "grid": list(spec.grid_shape), "slabs": len(log) if world == 1 else len(slabs), "world": world,
            "total_pairs": sum(s["pairs"] for s in log), "valid_pixels": int((~torch.isnan(colmax)).sum().item()),
            "colmax_sum": float(torch.nan_to_num(colmax).double().sum().item()), "per_slab": log}
+    if cappi is not None:
+        out.update(cappi_altitude=args.cappi, cappi_levels_owned_here=cappi_owned,
+                   cappi_valid_pixels=int((~torch.isnan(cappi)).sum().item()),
+                   cappi_sum=float(torch.nan_to_num(cappi).double().sum().item()))
     if args.check:
         whole = rg.DeviceGeometry.build(*dgates, spec.grid_shape, spec.grid_limits, min_radius=spec.min_radius,
                                         beam_factor=spec.beam_factor, weighting=spec.weighting, toa=spec.toa, ctx=ctx)
-        ref = rg.grid_fields(whole, [dfield], mask_invalid=True, want_grid=False, products=[rg.ColumnMax()], ctx=ctx)["products"][0]
+        prods = [rg.ColumnMax()] + ([] if cappi_req is None else [cappi_req])
+        refs = rg.grid_fields(whole, [dfield], mask_invalid=True, want_grid=False, products=prods, ctx=ctx)["products"]
+        ref = refs[0]
+        if cappi is not None:
+            out["cappi_identical_to_unsharded"] = bool(torch.equal(torch.nan_to_num(refs[1], nan=-1e30),
+                                                                   torch.nan_to_num(cappi, nan=-1e30)))
         out["identical_to_unsharded"] = bool(torch.equal(torch.nan_to_num(ref, nan=-1e30), torch.nan_to_num(colmax, nan=-1e30)))
     if rank == 0:
         print(json.dumps(out))

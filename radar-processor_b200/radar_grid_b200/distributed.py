@@ -11,6 +11,9 @@ multiprocessing.Pool over z-levels inside the table build, compute.py:203-222):
                  holds only its slab (`zslab_ranges`), grids it, and the partial COLMAX planes are combined by
                  ONE all-reduce(max) over NCCL/NVLink (`allreduce_nanmax`; NaN = "no data" is carried as -inf
                  because max(NaN, x) is unspecified in NCCL).  3-D grids need no exchange: slabs concatenate.
+                 A CAPPI blends two adjacent levels that may sit in different slabs: every rank contributes
+                 weight x level for the levels it owns and ONE all-reduce(sum) finishes the blend
+                 (`cappi_zslab`; bit-identical to the unsharded CAPPI, see there).
 
 The collective helpers work on CPU tensors with the gloo backend too, which is how the host-side logic is
 tested without GPUs.
@@ -100,3 +103,71 @@ def colmax_zslab(grid_slab: Callable[[], "object"], group=None):
     e.g. from ``grid_fields(slab_geometry, ..., products=[ColumnMax()], want_grid=False)``; the result is the
     global COLMAX on every rank."""
     return allreduce_nanmax(grid_slab(), group=group)
+
+
+def cappi_zslab_terms(request, grid_shape, grid_limits, z_range):
+    """
+    Split a CAPPI request (engine.CAPPI; reference products.py:317-415) over z-slabs.
+
+    Returns None when the altitude is outside the grid (all-NaN plane, products.py:370-372), else
+    ``(terms, dtype)``: ``terms`` = [(global level, weight)] for the levels inside ``z_range`` = [z0, z1) — none, one
+    or two entries — and ``dtype`` the arithmetic type of the blend (float32, or float64 when the grid limits are
+    NumPy scalars; see engine.CAPPI.resolve).  A level pick (nearest / exact level / clamped) is one term of weight 1.
+    """
+    from . import _native as N
+    pr, _ = request.resolve(grid_shape, grid_limits, True)
+    if pr is None:
+        return None
+    if pr.mode == N.RG_BLEND_PICK:
+        parts, dtype = [(int(pr.z_lo), 1.0)], np.float32
+    else:
+        parts = [(int(pr.z_lo), float(pr.w_lo)), (int(pr.z_hi), float(pr.w_hi))]
+        dtype = np.float32 if pr.mode == N.RG_BLEND_F32 else np.float64
+    z0, z1 = int(z_range[0]), int(z_range[1])
+    return [(z, w) for z, w in parts if z0 <= z < z1], dtype
+
+
+def cappi_zslab_partial(request, grid_shape, grid_limits, z_range, level_planes: Callable[[List[int]], Sequence], like):
+    """This rank's contribution to a z-slab CAPPI, before the all-reduce: ``sum(weight * plane)`` over the levels
+    it owns, in the blend's arithmetic type, starting from -0.0 (the neutral element of IEEE addition, signed zeros
+    included).  None when the altitude is outside the grid.  Arguments as in `cappi_zslab`."""
+    import torch
+    plan = cappi_zslab_terms(request, grid_shape, grid_limits, z_range)
+    if plan is None:
+        return None
+    terms, dtype = plan
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    acc = torch.full_like(like, -0.0, dtype=tdt)
+    if terms:
+        planes = level_planes([z for z, _ in terms])
+        if len(planes) != len(terms):
+            raise ValueError("level_planes returned a different number of planes than levels asked for")
+        for (z, w), plane in zip(terms, planes):
+            plane = plane.to(tdt)
+            acc += plane if w == 1.0 else plane * w
+    return acc
+
+
+def cappi_zslab(request, grid_shape, grid_limits, z_range, level_planes: Callable[[List[int]], Sequence], like,
+                group=None):
+    """
+    CAPPI of a grid that is split into z-slabs across ranks; the result is the global plane on every rank.
+
+    ``level_planes(levels)`` returns this rank's planes (torch tensors shaped like ``like``, float32, NaN = no data)
+    for the GLOBAL level indices asked for — normally a closure over
+    ``grid_fields(slab_geometry, ..., products=[LevelPick(z) for z in levels], want_grid=False)``, so the levels
+    come out of the same fused pass as the slab's COLMAX; it is not called on ranks that own neither level.
+    ``like`` is a tensor giving shape and device of a plane (F, ny, nx).
+
+    Every rank forms its partial blend (`cappi_zslab_partial`) and one all-reduce(sum) adds the at most two
+    non-neutral contributions: ``w_lo*g[lo] + w_hi*g[hi]`` with one rounding per operation, exactly the reference's
+    expression (products.py:411), NaN in either level giving NaN.  Weight-1 picks skip the multiplication.
+    """
+    import torch
+    dist = _dist()
+    acc = cappi_zslab_partial(request, grid_shape, grid_limits, z_range, level_planes, like)
+    if acc is None:
+        return torch.full_like(like, float("nan"), dtype=torch.float32)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
+    return acc.to(torch.float32)

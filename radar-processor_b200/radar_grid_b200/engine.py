@@ -242,6 +242,19 @@ class CAPPI:
 
 
 @dataclass
+class LevelPick:
+    """One level of the grid by its GLOBAL index (0 .. nz-1).  Not a reference product by itself: it is the term a
+    z-slab contributes to a CAPPI whose two levels live in different slabs (distributed.cappi_zslab)."""
+    level: int
+    name = "level"
+
+    def resolve(self, grid_shape, grid_limits, have_geometry=True):
+        if not (0 <= int(self.level) < grid_shape[0]):
+            raise ValueError(f"level {self.level} outside the grid (nz = {grid_shape[0]})")
+        return N.Product(kind=N.RG_PROD_LEVEL, mode=N.RG_BLEND_PICK, z_lo=int(self.level)), np.float32
+
+
+@dataclass
 class PPI:
     """constant_elevation_ppi — reference products.py:168-314."""
     elevation_angle: float

@@ -60,6 +60,37 @@ def _worker(rank, world, port, out_dir):
         assert np.array_equal(full, g["colmax"], equal_nan=True), "z-slab COLMAX != reference COLMAX"
         pmin = torch.from_numpy(O.column_reduce("min", slab).copy())
         assert np.array_equal(D.allreduce_nanmax(pmin, minimum=True).numpy(), g["colmin"], equal_nan=True)
+        # --- z-slab CAPPI: levels in different slabs, one all-reduce(sum); bit-identical to the unsharded CAPPI
+        from radar_grid_b200 import CAPPI
+        grid = g["grid_DBZH"]
+        like = torch.empty((1, ny, nx))
+        z_top = spec.grid_limits[0][1]
+        step = z_top / (nz - 1)
+        boundary = D.zslab_ranges(nz, world)[0][1]                      # first level of rank 1
+        lims64 = tuple(tuple(np.float64(v) for v in ax) for ax in spec.grid_limits)      # float64 blend
+        cases = [(CAPPI((boundary - 0.6) * step), spec.grid_limits),    # lo on rank 0, hi on rank 1
+                 (CAPPI((boundary - 0.6) * step), lims64),
+                 (CAPPI(0.3 * step), spec.grid_limits),                 # both levels on rank 0
+                 (CAPPI((nz - 1.5) * step), spec.grid_limits),          # both on the last rank
+                 (CAPPI(boundary * step), spec.grid_limits),            # exact level
+                 (CAPPI((boundary - 0.4) * step, "nearest"), spec.grid_limits),
+                 (CAPPI(z_top + 1.0), spec.grid_limits)]                # outside: all NaN
+        for req, lims in cases:
+            asked = []
+
+            def level_planes(levels):
+                asked.extend(levels)
+                assert all(z0 <= z < z1 for z in levels), "asked for a level outside the slab"
+                return [torch.from_numpy(grid[z][None].copy()) for z in levels]
+
+            got = D.cappi_zslab(req, spec.grid_shape, lims, (z0, z1), level_planes, like).numpy()[0]
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                want = O.cappi(grid, spec.grid_shape, lims, req.altitude, req.interpolation)
+            assert got.dtype == np.float32 and np.array_equal(got, np.asarray(want, dtype=np.float32), equal_nan=True), \
+                f"z-slab CAPPI {req} != unsharded CAPPI"
+            assert np.array_equal(np.signbit(got), np.signbit(np.asarray(want, dtype=np.float32)))
         # --- volume batch: each rank grids its share, rank 0 gathers
         ids = D.shard_volumes(5, world, rank)
         local = D.grid_volume_batch(ids, lambda vid: vid, lambda v: np.full((2, 2), float(v)))

@@ -273,6 +273,58 @@ def _zslab_checks(spec, gates, names, data, masks, whole, D, torch):
     assert_same(one.numpy(), full["products"][0])
 
 
+def test_zslab_cappi_two_party_sum_is_bit_identical():
+    """A CAPPI whose two levels sit in different z-slabs: every slab contributes weight x level for the
+    levels it owns, out of the same fused pass as its COLMAX (LevelPick), and the sum of the contributions — what
+    all_reduce(SUM) does across ranks — is the unsharded fused CAPPI bit for bit, for the float32 and float64 blends,
+    level picks and the out-of-range NaN plane."""
+    import torch
+    from radar_grid_b200 import distributed as D
+    spec, radar, gates, fields, g = golden_case("small")
+    names = list(fields)
+    data = [np.ma.getdata(fields[n]) for n in names]
+    masks = [np.ma.getmaskarray(fields[n]) for n in names]
+    nz, ny, nx = spec.grid_shape
+    z_top = spec.grid_limits[0][1]
+    step = z_top / (nz - 1)
+    ranges = D.zslab_ranges(nz, 3)
+    b = ranges[0][1]
+    lims64 = tuple(tuple(np.float64(v) for v in ax) for ax in spec.grid_limits)
+    whole = build(spec, gates, "barnes2", 0)
+    whole.ctx.set_option("group_width", 8)           # same summation order for slabs and whole grid, as above
+    try:
+        slabs = [build(spec, gates, "barnes2", 0, z_range=zr) for zr in ranges]
+        like = torch.empty((len(names), ny, nx))
+        for alt, interp, lims in [((b - 0.6) * step, "linear", spec.grid_limits), ((b - 0.6) * step, "linear", lims64),
+                                  ((ranges[1][1] - 0.25) * step, "linear", spec.grid_limits),
+                                  (0.3 * step, "linear", spec.grid_limits), (b * step, "linear", spec.grid_limits),
+                                  ((b - 0.4) * step, "nearest", spec.grid_limits), (z_top + 5.0, "linear", spec.grid_limits)]:
+            req = rg.CAPPI(alt, interp)
+            whole.grid_limits = lims
+            want = rg.grid_fields(whole, data, masks=masks, want_grid=False, products=[req])["products"][0]
+            total, owners = None, 0
+            for zr, slab in zip(ranges, slabs):
+                def level_planes(levels, slab=slab):
+                    r = rg.grid_fields(slab, data, masks=masks, want_grid=False,
+                                       products=[rg.ColumnMax()] + [rg.LevelPick(z) for z in levels])
+                    return [torch.from_numpy(p.copy()) for p in r["products"][1:]]
+                terms = D.cappi_zslab_terms(req, spec.grid_shape, lims, zr)
+                owners += 0 if terms is None else len(terms[0])
+                part = D.cappi_zslab_partial(req, spec.grid_shape, lims, zr, level_planes, like)
+                if part is not None:
+                    total = part if total is None else total + part          # what all_reduce(SUM) does
+            if total is None:                                                # outside the grid on every rank
+                total = D.cappi_zslab(req, spec.grid_shape, lims, ranges[0], None, like)
+            got = total.to(torch.float32).numpy()
+            assert_same(got, want, f"z-slab CAPPI {alt} {interp}")
+            assert np.array_equal(np.signbit(got), np.signbit(want))
+            if alt <= z_top:
+                assert owners == (1 if (interp == "nearest" or alt == b * step) else 2)
+    finally:
+        whole.grid_limits = spec.grid_limits
+        whole.ctx.set_option("group_width", 0)
+
+
 def test_device_buffers_match_host_buffers():
     """torch CUDA tensors in / out (zero-copy, RG_DEVICE) give bit-identical results to NumPy buffers (RG_HOST)."""
     torch = pytest.importorskip("torch")
