@@ -145,8 +145,11 @@ def run_b200(args):
     if N.device_count() < 1 or not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: radar_grid_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    affinity = {"bound": False, "why": "single rank"}
     if world > 1:
         import torch.distributed as dist
+        from radar_grid_b200 import distributed as D
+        affinity = D.bind_host_to_gpu(local_rank)       # before any pinned buffer exists (first-touch placement)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     spec = S.SPECS[args.workload]
@@ -274,6 +277,7 @@ def run_b200(args):
             "pairs": P, "voxels": V, "gates": G, "fields": F,
             "l2_policy": "inputs larger than L2 (8P-byte pair stream = %.2f GB per step)" % (8 * P / 1e9),
             "parallelism": f"volume-batch shard x{world}, table replicated, no data-path collective",
+            "host_affinity_rank0": affinity,
             "geometry_build_ms_device": info["build_ms"], "geometry_build_s_wall": build_wall,
             "geometry_candidates_per_pair": info["n_candidates"] / max(P, 1),
             "pack_ms_per_step": pack_ms / max(n_pack, 1), "apply_ms_per_step": apply_avg_ms,

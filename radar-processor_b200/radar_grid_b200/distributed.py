@@ -13,7 +13,9 @@ multiprocessing.Pool over z-levels inside the table build, compute.py:203-222):
                  because max(NaN, x) is unspecified in NCCL).  3-D grids need no exchange: slabs concatenate.
                  A CAPPI blends two adjacent levels that may sit in different slabs: every rank contributes
                  weight x level for the levels it owns and ONE all-reduce(sum) finishes the blend
-                 (`cappi_zslab`; bit-identical to the unsharded CAPPI, see there).
+                 (`cappi_zslab`; bit-identical to the unsharded CAPPI, see there).  A PPI follows the beam, so
+                 its level pair differs per pixel: every rank gathers, from its slab's 3-D grid, the levels it
+                 owns pixel by pixel and the same all-reduce(sum) finishes the blend (`ppi_zslab`).
 
 The collective helpers work on CPU tensors with the gloo backend too, which is how the host-side logic is
 tested without GPUs.
@@ -171,3 +173,122 @@ def cappi_zslab(request, grid_shape, grid_limits, z_range, level_planes: Callabl
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
     return acc.to(torch.float32)
+
+
+def ppi_zslab_plan(request, grid_shape, grid_limits):
+    """
+    Per-pixel level pair and weights of a constant-elevation PPI (engine.PPI) — the host-side half of
+    reference products.py:227-309, in the reference's own dtypes: float32 pixel coordinates and horizontal distance,
+    float64 beam height (radar_altitude 0: heights are relative to the radar), float64 fractional level.
+
+    linear : {"lo", "hi"} int64 (ny, nx) clipped to [0, nz-1], {"w_lo", "w_hi"} float64, "nan" bool (beam below /
+             above the grid, products.py:306-309)
+    nearest: {"lo"} = round(z_frac) clipped, "nan" = index outside [0, nz) (products.py:263-272)
+    """
+    from .products import compute_beam_height, compute_beam_height_flat
+    if request.interpolation not in ("linear", "nearest"):
+        raise ValueError(f"Unknown interpolation method: {request.interpolation}")
+    nz, ny, nx = grid_shape
+    z_min, z_max = grid_limits[0]
+    yc = np.linspace(grid_limits[1][0], grid_limits[1][1], ny, dtype="float32")
+    xc = np.linspace(grid_limits[2][0], grid_limits[2][1], nx, dtype="float32")
+    yy, xx = np.meshgrid(yc, xc, indexing="ij")
+    hdist = np.sqrt(xx ** 2 + yy ** 2)
+    tz = (compute_beam_height(hdist, request.elevation_angle, 0.0, request.ke) if request.earth_curvature
+          else compute_beam_height_flat(hdist, request.elevation_angle, 0.0))
+    z_step = (z_max - z_min) / (nz - 1) if nz > 1 else 1.0
+    z_frac = (tz - z_min) / z_step
+    if request.interpolation == "nearest":
+        zi = np.round(z_frac).astype(np.int64)
+        return {"mode": "nearest", "lo": np.clip(zi, 0, nz - 1), "nan": ~((zi >= 0) & (zi < nz))}
+    lo = np.floor(z_frac).astype(np.int64)
+    w_hi = z_frac - lo
+    return {"mode": "linear", "lo": np.clip(lo, 0, nz - 1), "hi": np.clip(lo + 1, 0, nz - 1),
+            "w_lo": 1.0 - w_hi, "w_hi": w_hi, "nan": (tz < z_min) | (tz > z_max)}
+
+
+def ppi_zslab_partial(plan, z_range, slab_grids):
+    """This rank's contribution to a z-slab PPI: ``slab_grids`` is a torch tensor (F, z1-z0, ny, nx) float32 (the
+    slab's 3-D grids, NaN = no data); per pixel the owned levels of the pair are gathered and weighted, levels of
+    other slabs contribute -0.0 (neutral for IEEE addition), pixels the beam leaves the grid at are NaN on every
+    rank.  float64 (F, ny, nx) for 'linear' — the reference returns float64 there — float32 for 'nearest'."""
+    import torch
+    z0, z1 = int(z_range[0]), int(z_range[1])
+    dev = slab_grids.device
+    F, nzs = slab_grids.shape[0], slab_grids.shape[1]
+    if nzs != z1 - z0:
+        raise ValueError("slab_grids does not have z1 - z0 levels")
+
+    def pick(levels):
+        lv = torch.from_numpy(levels).to(dev)
+        own = (lv >= z0) & (lv < z1)
+        idx = (lv - z0).clamp_(0, max(nzs - 1, 0))
+        vals = torch.gather(slab_grids, 1, idx.expand(F, 1, *idx.shape)).squeeze(1) if nzs > 0 else \
+            torch.zeros((F,) + tuple(lv.shape), device=dev)
+        return own, vals
+
+    nan = torch.from_numpy(plan["nan"]).to(dev)
+    if plan["mode"] == "nearest":
+        own, v = pick(plan["lo"])
+        out = torch.where(own, v, torch.full_like(v, -0.0))
+    else:
+        own_lo, v_lo = pick(plan["lo"])
+        own_hi, v_hi = pick(plan["hi"])
+        w_lo, w_hi = torch.from_numpy(plan["w_lo"]).to(dev), torch.from_numpy(plan["w_hi"]).to(dev)
+        neutral = torch.full(v_lo.shape, -0.0, dtype=torch.float64, device=dev)
+        out = torch.where(own_lo, w_lo * v_lo.double(), neutral) + torch.where(own_hi, w_hi * v_hi.double(), neutral)
+    out.masked_fill_(nan, float("nan"))
+    return out
+
+
+def ppi_zslab(request, grid_shape, grid_limits, z_range, slab_grids, group=None):
+    """Constant-elevation PPI of a grid split into z-slabs: `ppi_zslab_partial` on every rank, then ONE
+    all-reduce(sum) of the (F, ny, nx) planes — per pixel ``w_lo*g[lo] + w_hi*g[hi]`` with the reference's roundings
+    (products.py:294-304), whichever ranks hold the two levels.  The global plane is returned on every rank."""
+    dist = _dist()
+    out = ppi_zslab_partial(ppi_zslab_plan(request, grid_shape, grid_limits), z_range, slab_grids)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+    return out
+
+
+def parse_cpulist(text: str) -> List[int]:
+    """'0-3,8,10-11' (the sysfs cpulist format) -> [0, 1, 2, 3, 8, 10, 11]."""
+    cpus: List[int] = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.extend(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_host_to_gpu(device_index: int, sysfs_root: str = "/sys/bus/pci/devices") -> Dict[str, object]:
+    """
+    Pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE pinned host buffers are allocated: with
+    one process per GPU the end-to-end path moves ~300 MB per volume between pinned host memory and the device, and
+    first-touch places those pages on the node of the allocating thread — the wrong socket for half the GPUs of an
+    8-GPU box unless the process is bound.  Best effort: returns what it did ({"bound": False, "why": ...} when the
+    topology cannot be read), never raises.
+    """
+    import os
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(os.path.join(sysfs_root, bdf, "local_cpulist")) as fh:
+            local = parse_cpulist(fh.read())
+        try:
+            with open(os.path.join(sysfs_root, bdf, "numa_node")) as fh:
+                node = int(fh.read().strip())
+        except OSError:
+            node = -1
+        allowed = sorted(set(local) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return {"bound": False, "why": "no local CPU in this process's affinity mask", "pci": bdf, "numa_node": node}
+        if len(allowed) == len(os.sched_getaffinity(0)):
+            return {"bound": False, "why": "single NUMA domain (every allowed CPU is local)", "pci": bdf, "numa_node": node}
+        os.sched_setaffinity(0, allowed)
+        return {"bound": True, "pci": bdf, "numa_node": node, "cpus": len(allowed)}
+    except Exception as e:  # noqa: BLE001 — topology files differ between boxes; binding is an optimisation only
+        return {"bound": False, "why": f"{type(e).__name__}: {e}"}

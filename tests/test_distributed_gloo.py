@@ -91,6 +91,17 @@ def _worker(rank, world, port, out_dir):
             assert got.dtype == np.float32 and np.array_equal(got, np.asarray(want, dtype=np.float32), equal_nan=True), \
                 f"z-slab CAPPI {req} != unsharded CAPPI"
             assert np.array_equal(np.signbit(got), np.signbit(np.asarray(want, dtype=np.float32)))
+        # --- z-slab PPI: per-pixel level pairs, gathered from the slab's grid, one all-reduce(sum)
+        from radar_grid_b200 import PPI
+        slab_t = torch.from_numpy(grid[z0:z1][None].copy())
+        for el in (0.5, 6.0, 20.0):
+            for interp in ("linear", "nearest"):
+                for curved in (True, False):
+                    req = PPI(el, interp, curved)
+                    got = D.ppi_zslab(req, spec.grid_shape, spec.grid_limits, (z0, z1), slab_t).numpy()[0]
+                    want = O.ppi(grid, spec.grid_shape, spec.grid_limits, el, interp, curved)
+                    assert got.dtype == want.dtype and np.array_equal(got, want, equal_nan=True), f"z-slab PPI {req}"
+                    assert np.array_equal(np.signbit(got), np.signbit(want))
         # --- volume batch: each rank grids its share, rank 0 gathers
         ids = D.shard_volumes(5, world, rank)
         local = D.grid_volume_batch(ids, lambda vid: vid, lambda v: np.full((2, 2), float(v)))
@@ -114,3 +125,11 @@ def test_allreduce_nanmax_single_process_semantics():
     p = torch.tensor([[1.0, float("nan")], [float("nan"), -2.0]])
     out = D.allreduce_nanmax(p.clone())
     assert torch.equal(torch.isnan(out), torch.isnan(p)) and out[0, 0] == 1.0 and out[1, 1] == -2.0
+
+
+def test_cpulist_parsing_and_best_effort_binding(tmp_path):
+    assert D.parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert D.parse_cpulist("5") == [5] and D.parse_cpulist("") == []
+    before = os.sched_getaffinity(0)
+    r = D.bind_host_to_gpu(0, sysfs_root=str(tmp_path))        # no GPU / no topology here: reports, never raises
+    assert r["bound"] is False and "why" in r and os.sched_getaffinity(0) == before

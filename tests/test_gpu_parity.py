@@ -325,6 +325,40 @@ def test_zslab_cappi_two_party_sum_is_bit_identical():
         whole.ctx.set_option("group_width", 0)
 
 
+def test_zslab_ppi_partial_blends_sum_to_the_fused_ppi():
+    """PPI over z-slabs: per pixel every slab weights the levels of the beam's pair that it owns, gathered
+    from its own 3-D grid on the device; the sum of the partial planes (all_reduce(SUM) across ranks) is the fused PPI
+    of the unsharded grid bit for bit — float64 for 'linear', float32 for 'nearest', NaN where the beam leaves the grid."""
+    import torch
+    from radar_grid_b200 import distributed as D
+    spec, radar, gates, fields, g = golden_case("small")
+    names = list(fields)
+    data = [torch.from_numpy(np.ma.getdata(fields[n]).copy()).cuda() for n in names]
+    masks = [torch.from_numpy(np.ma.getmaskarray(fields[n]).copy()).cuda() for n in names]
+    ranges = D.zslab_ranges(spec.grid_shape[0], 3)
+    whole = build(spec, gates, "barnes2", 0)
+    whole.ctx.set_option("group_width", 8)           # same summation order for slabs and whole grid, as above
+    try:
+        slab_grids = []
+        for zr in ranges:
+            slab = build(spec, gates, "barnes2", 0, z_range=zr)
+            slab_grids.append(torch.stack(rg.grid_fields(slab, data, masks=masks)["grids"]))
+        for el, interp, curved in [(0.5, "linear", True), (4.0, "linear", True), (4.0, "nearest", True),
+                                   (12.0, "linear", False), (30.0, "nearest", False)]:
+            req = rg.PPI(el, interp, curved)
+            want = rg.grid_fields(whole, data, masks=masks, want_grid=False, products=[req])["products"][0]
+            plan = D.ppi_zslab_plan(req, spec.grid_shape, spec.grid_limits)
+            total = None
+            for zr, sg in zip(ranges, slab_grids):
+                part = D.ppi_zslab_partial(plan, zr, sg)
+                assert part.is_cuda
+                total = part if total is None else total + part
+            assert_same(total.cpu().numpy(), want.cpu().numpy(), f"z-slab PPI {el} {interp}")
+            assert int((~torch.isnan(want)).sum()) > 0
+    finally:
+        whole.ctx.set_option("group_width", 0)
+
+
 def test_device_buffers_match_host_buffers():
     """torch CUDA tensors in / out (zero-copy, RG_DEVICE) give bit-identical results to NumPy buffers (RG_HOST)."""
     torch = pytest.importorskip("torch")
