@@ -219,3 +219,37 @@ def test_geometry_cache_keys_and_lru_eviction():
     assert cache.get(gx, gy, gz, (2, 3, 5), LIM, min_radius=250.0, weighting="barnes2") is not a   # grid changed
     cache.clear()
     assert cache.bytes_held() == 0
+
+
+def test_zslab_product_plans():
+    """Host half of the z-slab CAPPI / PPI (distributed.py): which slab owns which level, with which weight."""
+    from radar_grid_b200 import distributed as D
+    shape, limits = (10, 5, 7), ((0.0, 9000.0), (-2000.0, 2000.0), (-3000.0, 3000.0))
+    # linear blend between levels 3 and 4, slabs [0,4) and [4,10): one term each, weights of the unsharded resolve
+    pr, _ = rg.CAPPI(3250.0).resolve(shape, limits)
+    lo, dt = D.cappi_zslab_terms(rg.CAPPI(3250.0), shape, limits, (0, 4))
+    hi, _ = D.cappi_zslab_terms(rg.CAPPI(3250.0), shape, limits, (4, 10))
+    assert dt == np.float32 and lo == [(3, pr.w_lo)] and hi == [(4, pr.w_hi)]
+    assert D.cappi_zslab_terms(rg.CAPPI(3250.0), shape, limits, (5, 10))[0] == []
+    # exact level and nearest: a single weight-1 pick on the owner only
+    assert D.cappi_zslab_terms(rg.CAPPI(4000.0), shape, limits, (4, 10))[0] == [(4, 1.0)]
+    assert D.cappi_zslab_terms(rg.CAPPI(4000.0), shape, limits, (0, 4))[0] == []
+    assert D.cappi_zslab_terms(rg.CAPPI(3600.0, "nearest"), shape, limits, (4, 10))[0] == [(4, 1.0)]
+    # NumPy-scalar limits promote the blend to float64 (as in CAPPI.resolve); outside the grid: no plan at all
+    lims64 = tuple(tuple(np.float64(v) for v in ax) for ax in limits)
+    assert D.cappi_zslab_terms(rg.CAPPI(3250.0), shape, lims64, (0, 10))[1] == np.float64
+    assert D.cappi_zslab_terms(rg.CAPPI(9500.0), shape, limits, (0, 10)) is None
+    with pytest.raises(ValueError):
+        D.cappi_zslab_terms(rg.CAPPI(3250.0, "cubic"), shape, limits, (0, 10))
+    with pytest.raises(ValueError):
+        rg.LevelPick(10).resolve(shape, limits)
+    assert rg.LevelPick(9).resolve(shape, limits)[0].z_lo == 9
+    # PPI plan: shapes, dtypes, weights sum to one, clipped levels
+    plan = D.ppi_zslab_plan(rg.PPI(20.0), shape, limits)
+    assert plan["mode"] == "linear" and plan["lo"].shape == (5, 7) and plan["w_lo"].dtype == np.float64
+    np.testing.assert_allclose(plan["w_lo"] + plan["w_hi"], 1.0, rtol=0, atol=1e-15)
+    assert plan["lo"].min() >= 0 and plan["hi"].max() <= 9 and plan["nan"].dtype == np.bool_
+    near = D.ppi_zslab_plan(rg.PPI(89.0, "nearest"), shape, limits)
+    assert near["mode"] == "nearest" and near["nan"].any()          # a near-vertical beam leaves the grid top
+    with pytest.raises(ValueError):
+        D.ppi_zslab_plan(rg.PPI(1.0, "cubic"), shape, limits)
