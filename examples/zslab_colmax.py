@@ -31,6 +31,8 @@ def main():
     ap.add_argument("--slabs", type=int, default=8)
     ap.add_argument("--cappi", type=float, default=None, metavar="ALT_M",
                     help="also a CAPPI at this altitude: level picks out of the same pass, one all-reduce(sum)")
+    ap.add_argument("--ppi", type=float, default=None, metavar="ELEV_DEG",
+                    help="also a PPI at this elevation: partial blends from each slab's 3-D grid, one all-reduce(sum)")
     ap.add_argument("--check", action="store_true", help="also build the whole grid in one piece and compare (small specs)")
     args = ap.parse_args()
 
@@ -61,6 +63,9 @@ def main():
     partial = torch.full((1, ny, nx), float("nan"), device="cuda")
     cappi_req = None if args.cappi is None else rg.CAPPI(args.cappi)
     cappi_acc, cappi_owned = None, []
+    ppi_req = None if args.ppi is None else rg.PPI(args.ppi)
+    ppi_plan = None if ppi_req is None else D.ppi_zslab_plan(ppi_req, spec.grid_shape, spec.grid_limits)
+    ppi_acc = None
     log = []
     todo = list(mine)
     while todo:
@@ -83,9 +88,12 @@ def main():
         if cappi_req is not None:
             plan = D.cappi_zslab_terms(cappi_req, spec.grid_shape, spec.grid_limits, (z0, z1))
             levels = [] if plan is None else [z for z, _ in plan[0]]
-        res = rg.grid_fields(geom, [dfield], mask_invalid=True, want_grid=False,
+        res = rg.grid_fields(geom, [dfield], mask_invalid=True, want_grid=ppi_req is not None,
                              products=[rg.ColumnMax()] + [rg.LevelPick(z) for z in levels], ctx=ctx)
         ctx.synchronize()
+        if ppi_req is not None:                               # the beam's level pair differs per pixel: from the slab grid
+            part = D.ppi_zslab_partial(ppi_plan, (z0, z1), torch.stack(res["grids"]))
+            ppi_acc = part if ppi_acc is None else ppi_acc + part
         if levels:
             part = D.cappi_zslab_partial(cappi_req, spec.grid_shape, spec.grid_limits, (z0, z1),
                                          lambda lv: res["products"][1:], partial)
@@ -111,6 +119,13 @@ def main():
             if world > 1:
                 dist.all_reduce(cappi_acc, op=dist.ReduceOp.SUM)      # the two-party sum of SURVEY 8e
             cappi = cappi_acc.to(torch.float32)
+    ppi = None
+    if ppi_req is not None:
+        if ppi_acc is None:
+            ppi_acc = D.ppi_zslab_partial(ppi_plan, (0, 0), torch.empty((1, 0, ny, nx), device="cuda"))
+        if world > 1:
+            dist.all_reduce(ppi_acc, op=dist.ReduceOp.SUM)
+        ppi = ppi_acc
     torch.cuda.synchronize()
 
     out = {"spec": spec.name, "grid": list(spec.grid_shape), "slabs": len(log) if world == 1 else len(slabs), "world": world,
@@ -120,15 +135,21 @@ def main():
         out.update(cappi_altitude=args.cappi, cappi_levels_owned_here=cappi_owned,
                    cappi_valid_pixels=int((~torch.isnan(cappi)).sum().item()),
                    cappi_sum=float(torch.nan_to_num(cappi).double().sum().item()))
+    if ppi is not None:
+        out.update(ppi_elevation=args.ppi, ppi_dtype=str(ppi.dtype), ppi_valid_pixels=int((~torch.isnan(ppi)).sum().item()),
+                   ppi_sum=float(torch.nan_to_num(ppi).double().sum().item()))
     if args.check:
         whole = rg.DeviceGeometry.build(*dgates, spec.grid_shape, spec.grid_limits, min_radius=spec.min_radius,
                                         beam_factor=spec.beam_factor, weighting=spec.weighting, toa=spec.toa, ctx=ctx)
-        prods = [rg.ColumnMax()] + ([] if cappi_req is None else [cappi_req])
+        prods = [rg.ColumnMax()] + ([] if cappi_req is None else [cappi_req]) + ([] if ppi_req is None else [ppi_req])
         refs = rg.grid_fields(whole, [dfield], mask_invalid=True, want_grid=False, products=prods, ctx=ctx)["products"]
         ref = refs[0]
         if cappi is not None:
             out["cappi_identical_to_unsharded"] = bool(torch.equal(torch.nan_to_num(refs[1], nan=-1e30),
                                                                    torch.nan_to_num(cappi, nan=-1e30)))
+        if ppi is not None:
+            out["ppi_identical_to_unsharded"] = bool(refs[-1].dtype == ppi.dtype and torch.equal(
+                torch.nan_to_num(refs[-1], nan=-1e30), torch.nan_to_num(ppi, nan=-1e30)))
         out["identical_to_unsharded"] = bool(torch.equal(torch.nan_to_num(ref, nan=-1e30), torch.nan_to_num(colmax, nan=-1e30)))
     if rank == 0:
         print(json.dumps(out))
