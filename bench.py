@@ -222,7 +222,7 @@ def run_b200(args):
         # Consecutive volumes go through VolumePipeline (3 contexts/streams), as a time series would: the H2D copy of
         # volume i+1 and the D2H copy of volume i-1 overlap the kernels of volume i.  Every volume is copied in full.
         e2e_steps = max(3, min(args.steps, args.e2e_steps))
-        n_slots = 3
+        n_slots = max(1, args.e2e_streams)
         pipe = rg.VolumePipeline(dev, n_streams=n_slots)
         slots = []
         for _ in range(n_slots):
@@ -292,7 +292,7 @@ def run_b200(args):
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
                 "single_call_ms": e2e_single_ms, "streams": n_slots,
                 "note": "pinned host fields in, 3-D grids + COLMAX + CAPPI planes back to pinned host memory, every volume "
-                        "copied in full; VolumePipeline -> grid_fields() -> rg_apply(RG_HOST) on 3 streams so that copies of "
+                        "copied in full; VolumePipeline -> grid_fields() -> rg_apply(RG_HOST) on several streams (see \"streams\") so that copies of "
                         "neighbouring volumes overlap the kernels"},
         "gpu_launches": launches,
     }
@@ -431,7 +431,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg1", "cfg2", "small", "tiny"])
-    ap.add_argument("--e2e-steps", type=int, default=24)
+    ap.add_argument("--e2e-steps", type=int, default=48)
+    ap.add_argument("--e2e-streams", type=int, default=3, help="contexts/streams of the end-to-end VolumePipeline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
