@@ -10,7 +10,7 @@ may import this module; the product package (``radar_grid_b200``) never does.
 Parity status: PINNED.  ``tests/golden/make_golden.py`` imports the real reference from
 ``/root/reference`` in the build container, runs it on the seeded synthetic volumes, and commits its
 outputs under ``tests/golden/``; ``tests/test_oracle_golden.py`` checks every function below against
-those vectors bit-exactly, and ``tests/test_oracle_known_answers.py`` replays the reference's own
+those vectors bit-exactly, and ``tests/test_known_answers.py`` replays the reference's own
 known-answer unit tests (tests/test_radar_grid_{interpolate,products,filters}.py) against it.
 
 Each function cites the reference lines it follows (paths relative to /root/reference).

@@ -141,6 +141,9 @@ void free_geometry(Geometry* g)
     cudaFree(g->sell);
     for (auto& qc : g->quad) { cudaFree(qc.quads); cudaFree(qc.ptr); }
     cudaFree(g->slice_base);
+    cudaFree(g->heavy_rows);
+    cudaFree(g->heavy_first);
+    cudaFree(g->heavy_chunks);
     cudaFree(g->x_ax);
     cudaFree(g->y_ax);
     cudaFree(g->z_ax);
@@ -337,7 +340,7 @@ int rg_context_destroy(rg_context* c)
     if (!ctx) return RG_OK;
     DeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (Scratch* s : {&ctx->records, &ctx->stage_in, &ctx->stage_out, &ctx->misc})
+    for (Scratch* s : {&ctx->records, &ctx->stage_in, &ctx->stage_out, &ctx->misc, &ctx->heavy})
         if (s->ptr) cudaFree(s->ptr);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

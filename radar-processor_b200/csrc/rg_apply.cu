@@ -31,14 +31,71 @@
 
 namespace rg {
 
+// Build-time switches: every design decision of K5 can be re-measured (tools/gpu_ab.sh, build.py --variant X -DRG_...).
+#ifndef RG_PREFETCH
+#define RG_PREFETCH 1          // levels of look-ahead for the L2 prefetch of the pair stream (0 = off)
+#endif
+#ifndef RG_TREDUCE
+#define RG_TREDUCE 1           // 1: reduce-scatter the row sums inside a group (14 shuffles), 0: plain butterfly (6F)
+#endif
+#ifndef RG_UNROLL
+#define RG_UNROLL 4            // pairs (and their gathers) in flight per lane
+#endif
+#ifndef RG_MINBLOCKS
+#define RG_MINBLOCKS (1024 / RG_APPLY_THREADS)     // 64 registers per thread: 32 resident warps per SM
+#endif
+#ifndef RG_TEX
+#define RG_TEX 0               // 1: gather the gate records through the texture path (tex1Dfetch) instead of LDG
+#endif
+
+#ifndef RG_REC32
+#define RG_REC32 1
+#endif
+
+#if RG_TEX && RG_REC32
+#error "the texture path fetches at most 16 bytes per texel: build RG_TEX variants with -DRG_REC32=0"
+#endif
+
 // ------------------------------------------------------------------------------------------------------
 // K4  pack: gate masks (field mask | masked_invalid | fused QC range rules) + AoS records
 // ------------------------------------------------------------------------------------------------------
-template <int FA, int FB>
+// Record layout per field count F (shared by K4, K5 and the exact kernel):
+//   F <= 4   one array A of FA = 1, 2 or 4 floats per gate; a masked value is the bit pattern kMaskedBits.
+//   F >= 5   RG_REC32 (default): ONE 32-byte record per gate, fetched with a single 256-bit load (LDG.E.256, new on
+//            sm_100): slots [0, F) hold the values with masked values stored as +0.0, slot 7 holds one mask bit per
+//            field (bit f set = field f masked) and the slots between carry the masks of the highest-numbered fields
+//            as floats (1.0 = valid, 0.0 = masked; F = 5: slot 5 = field 4, slot 6 = field 3; F = 6: slot 6 = field 5).
+//            Sums of w*v then need no predicate and pair up into packed FFMA2s, a mask float turns sum(w) into one
+//            more FFMA(2) lane, and the remaining fields take their predicates from the mask word with one R2P.
+//            F = 8 has no room for the mask word and keeps the marker scheme.
+//            Without RG_REC32: arrays A = float[G+1][4] and B = float[G+1][FB] (the round-1 layout, kept for A/B runs).
+template <int F>
+struct Layout {
+    static constexpr bool R32 = RG_REC32 && F >= 5;
+    static constexpr int FP = F == 1 ? 1 : F == 2 ? 2 : F <= 4 ? 4 : 8;
+    static constexpr int FA = R32 ? 8 : F == 1 ? 1 : F == 2 ? 2 : 4;
+    static constexpr int FB = R32 || F <= 4 ? 0 : F == 5 ? 1 : F == 6 ? 2 : 4;
+    static constexpr int NV = FA + FB;           // floats gathered per gate
+    static constexpr bool MB = R32 && F <= 7;    // mask bits in slot 7, masked values stored as 0
+    static constexpr int NMF = MB ? 7 - F : 0;   // mask floats in slots [F, 7): slot s belongs to field 2F - 1 - s
+    static constexpr int SH = F <= 6 ? 1 : 0;    // field f's mask bit is bit f + SH: R2P fills P1.. in one instruction, bit 0 costs two more
+};
+
+__device__ __forceinline__ void store_vec8(float* dst, const float* v)
+{
+#ifndef RG_EMU
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+#else
+    for (int i = 0; i < 8; ++i) dst[i] = v[i];
+#endif
+}
+
+template <int F>
 __global__ void __launch_bounds__(256) pack_records_kernel(const __grid_constant__ PackParams p)
 {
-    // FB == 0: one AoS array of FA floats per gate.  FB > 0: fields 0..FA-1 in array A, FA.. in array B.
-    constexpr int NV = FA + FB;
+    using L = Layout<F>;
+    constexpr int FA = L::FA, FB = L::FB, NV = L::NV;
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g > p.n_gates) return;
     const bool null_gate = g == p.n_gates;       // record n_gates is all-masked: a harmless target for idle lanes
@@ -52,27 +109,36 @@ __global__ void __launch_bounds__(256) pack_records_kernel(const __grid_constant
     }
 
     float out[NV];
+    uint32_t mask_bits = 0;
 #pragma unroll
-    for (int f = 0; f < NV; ++f) {
+    for (int f = 0; f < (L::MB ? F : NV); ++f) {
         uint32_t bits = kMaskedBits;
-        if (f < p.n_fields && !null_gate) {
+        if (f < F && !null_gate) {
             const float v = __ldg(p.fields[f] + g);
             bool masked = (excluded >> f) & 1u;
             if (p.masks[f] != nullptr) masked |= __ldg(p.masks[f] + g) != 0;
             if ((p.invalid_bits >> f) & 1u) masked |= !isfinite(v);          // np.ma.masked_invalid
             bits = masked ? kMaskedBits : (isnan(v) ? kCanonNaN : __float_as_uint(v));
         }
-        out[f] = __uint_as_float(bits);
+        if constexpr (L::MB) {
+            const bool m = bits == kMaskedBits;
+            mask_bits |= m ? (1u << (f + L::SH)) : 0u;
+            out[f] = m ? 0.f : __uint_as_float(bits);
+        } else {
+            out[f] = __uint_as_float(bits);
+        }
+    }
+    if constexpr (L::MB) {
+#pragma unroll
+        for (int s = F; s < 7; ++s) out[s] = (mask_bits >> (2 * F - 1 - s + L::SH)) & 1u ? 0.f : 1.f;
+        out[7] = __uint_as_float(mask_bits);
     }
     auto store = [](float* dst, const float* v, auto n) {
         constexpr int N = decltype(n)::value;
         if constexpr (N == 1) dst[0] = v[0];
         else if constexpr (N == 2) *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
         else if constexpr (N == 4) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-        else {
-            reinterpret_cast<float4*>(dst)[0] = make_float4(v[0], v[1], v[2], v[3]);
-            reinterpret_cast<float4*>(dst)[1] = make_float4(v[4], v[5], v[6], v[7]);
-        }
+        else store_vec8(dst, v);
     };
     store(p.records + (size_t)g * FA, out, std::integral_constant<int, FA>{});
     if constexpr (FB > 0) store(p.records_b + (size_t)g * FB, out + FA, std::integral_constant<int, FB>{});
@@ -82,7 +148,7 @@ __global__ void __launch_bounds__(256) pack_records_kernel(const __grid_constant
 int bind_record_textures(Context* ctx, const float* rec_a, const float* rec_b, int n_fields, int64_t n_gates)
 {
 #if RG_TEX && !defined(RG_EMU)
-    if (ctx->tex_a_ptr == rec_a && ctx->tex_b_ptr == rec_b && ctx->tex_fields == n_fields) return RG_OK;
+    if (ctx->tex_a_ptr == rec_a && ctx->tex_b_ptr == rec_b && ctx->tex_fields == n_fields && ctx->tex_gates == n_gates) return RG_OK;
     if (ctx->tex_a) { cudaDestroyTextureObject(ctx->tex_a); ctx->tex_a = 0; }
     if (ctx->tex_b) { cudaDestroyTextureObject(ctx->tex_b); ctx->tex_b = 0; }
     const int fa = n_fields == 1 ? 1 : n_fields == 2 ? 2 : 4;
@@ -102,7 +168,7 @@ int bind_record_textures(Context* ctx, const float* rec_a, const float* rec_b, i
     };
     RG_TRY(make(rec_a, fa, &ctx->tex_a));
     if (fb > 0) RG_TRY(make(rec_b, fb, &ctx->tex_b));
-    ctx->tex_a_ptr = rec_a; ctx->tex_b_ptr = rec_b; ctx->tex_fields = n_fields;
+    ctx->tex_a_ptr = rec_a; ctx->tex_b_ptr = rec_b; ctx->tex_fields = n_fields; ctx->tex_gates = n_gates;
 #else
     (void)ctx; (void)rec_a; (void)rec_b; (void)n_fields; (void)n_gates;
 #endif
@@ -113,7 +179,7 @@ int records_width(int n_fields) { return n_fields <= 1 ? 1 : n_fields == 2 ? 2 :
 
 size_t records_b_offset(int n_fields, int64_t n_gates)
 {
-    const int fa = n_fields == 1 ? 1 : n_fields == 2 ? 2 : 4;
+    const int fa = RG_REC32 && n_fields >= 5 ? 8 : n_fields == 1 ? 1 : n_fields == 2 ? 2 : 4;
     return (((size_t)(n_gates + 1) * fa * sizeof(float)) + 511) & ~(size_t)511;   // texture-bindable
 }
 
@@ -122,12 +188,14 @@ int launch_pack(Context* ctx, const PackParams& p)
     const unsigned blocks = (unsigned)((p.n_gates + 1 + 255) / 256);
     timer_begin(ctx, kTimerPack);
     switch (p.n_fields) {
-        case 1: pack_records_kernel<1, 0><<<blocks, 256, 0, ctx->stream>>>(p); break;
-        case 2: pack_records_kernel<2, 0><<<blocks, 256, 0, ctx->stream>>>(p); break;
-        case 3: case 4: pack_records_kernel<4, 0><<<blocks, 256, 0, ctx->stream>>>(p); break;
-        case 5: pack_records_kernel<4, 1><<<blocks, 256, 0, ctx->stream>>>(p); break;
-        case 6: pack_records_kernel<4, 2><<<blocks, 256, 0, ctx->stream>>>(p); break;
-        default: pack_records_kernel<4, 4><<<blocks, 256, 0, ctx->stream>>>(p); break;
+        case 1: pack_records_kernel<1><<<blocks, 256, 0, ctx->stream>>>(p); break;
+        case 2: pack_records_kernel<2><<<blocks, 256, 0, ctx->stream>>>(p); break;
+        case 3: pack_records_kernel<3><<<blocks, 256, 0, ctx->stream>>>(p); break;
+        case 4: pack_records_kernel<4><<<blocks, 256, 0, ctx->stream>>>(p); break;
+        case 5: pack_records_kernel<5><<<blocks, 256, 0, ctx->stream>>>(p); break;
+        case 6: pack_records_kernel<6><<<blocks, 256, 0, ctx->stream>>>(p); break;
+        case 7: pack_records_kernel<7><<<blocks, 256, 0, ctx->stream>>>(p); break;
+        default: pack_records_kernel<8><<<blocks, 256, 0, ctx->stream>>>(p); break;
     }
     timer_end(ctx, kTimerPack);
     ctx->launches++;
@@ -405,22 +473,6 @@ int launch_products(Context* ctx, const rg_grid_spec& grid, int n_fields, const 
 // 128-byte line of A.  (An interleaved 32-byte record and a two-lanes-per-record scheme were measured and lost,
 // see DESIGN.md section 6.)  The build-time switches below exist so that each design decision can be re-measured.
 // ------------------------------------------------------------------------------------------------------
-#ifndef RG_PREFETCH
-#define RG_PREFETCH 1          // levels of look-ahead for the L2 prefetch of the pair stream (0 = off)
-#endif
-#ifndef RG_TREDUCE
-#define RG_TREDUCE 1           // 1: reduce-scatter the row sums inside a group (14 shuffles), 0: plain butterfly (6F)
-#endif
-#ifndef RG_UNROLL
-#define RG_UNROLL 4            // pairs (and their gathers) in flight per lane
-#endif
-#ifndef RG_MINBLOCKS
-#define RG_MINBLOCKS (1024 / RG_APPLY_THREADS)     // 64 registers per thread: 32 resident warps per SM
-#endif
-#ifndef RG_TEX
-#define RG_TEX 0               // 1: gather the gate records through the texture path (tex1Dfetch) instead of LDG
-#endif
-
 #ifndef RG_FASTDIV
 #define RG_FASTDIV 1           // fast path: a * rcp(b) refined once (<= 1 ulp off IEEE) instead of the IEEE division sequence
 #endif
@@ -535,13 +587,6 @@ __device__ __forceinline__ void group4_reduce_scatter(const float (&swv)[F], con
     }
 }
 
-template <int F>
-struct Layout {
-    static constexpr int FP = F == 1 ? 1 : F == 2 ? 2 : F <= 4 ? 4 : 8;
-    static constexpr int FA = F == 1 ? 1 : F == 2 ? 2 : 4;
-    static constexpr int FB = F <= 4 ? 0 : F == 5 ? 1 : F == 6 ? 2 : 4;
-    static constexpr int NV = FA + FB;           // floats gathered per gate
-};
 
 template <int N>
 __device__ __forceinline__ void load_vec(const float* __restrict__ base, uint32_t gate, float* v)
@@ -555,11 +600,14 @@ __device__ __forceinline__ void load_vec(const float* __restrict__ base, uint32_
         const float4 t = __ldg(reinterpret_cast<const float4*>(base) + gate);
         v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
     } else if constexpr (N == 8) {
-        const float4* q = reinterpret_cast<const float4*>(base) + 2 * (size_t)gate;
-        const float4 a = __ldg(q);
-        const float4 b = __ldg(q + 1);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+#ifndef RG_EMU
+        // one 256-bit load (LDG.E.256, sm_100+): the whole 32-byte record of a gate in a single L1 request
+        asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+            : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+            : "l"(base + 8 * (size_t)gate));
+#else
+        for (int i = 0; i < 8; ++i) v[i] = base[8 * (size_t)gate + i];
+#endif
     }
 }
 
@@ -597,15 +645,49 @@ __device__ __forceinline__ void load_record(const RecSrc& r, uint32_t gate, floa
 #endif
 }
 
+// (a0, a1) += w * (v0, v1): one packed FFMA2 (fma.rn.f32x2, sm_100+) when the operands sit in register pairs, which
+// the 256-bit record load and the accumulator arrays give for free
+__device__ __forceinline__ void fma2(float& a0, float& a1, float w, float v0, float v1)
+{
+#ifndef RG_EMU
+    unsigned long long acc, vv, ww;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(acc) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(vv) : "f"(v0), "f"(v1));
+    asm("mov.b64 %0, {%1,%1};" : "=l"(ww) : "f"(w));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(ww), "l"(vv));
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(a0), "=f"(a1) : "l"(acc));
+#else
+    a0 = fmaf(w, v0, a0);
+    a1 = fmaf(w, v1, a1);
+#endif
+}
+
 template <int F, int NV>
 __device__ __forceinline__ void accumulate(float w, const float (&v)[NV], float (&swv)[F], float (&sw)[F])
 {
+    if constexpr (Layout<F>::MB) {
+        // 32-byte record: masked values are +0.0, so sum(w*v) needs no predicate (interpolate.py:78-82: masked gates
+        // contribute 0 to both sums).  Bit-identical to the predicated form: x + w*0 = x, fma(w, 1, x) = x + w.
+        constexpr int NMF = Layout<F>::NMF;
 #pragma unroll
-    for (int f = 0; f < F; ++f) {
-        const bool m = __float_as_uint(v[f]) == kMaskedBits;   // interpolate.py:78-79
-        if (!m) {                                              // predicated: ISETP + FADD + FFMA per field
-            sw[f] = __fadd_rn(sw[f], w);
-            swv[f] = fmaf(w, v[f], swv[f]);
+        for (int k = 0; k + 1 < F; k += 2) fma2(swv[k], swv[k + 1], w, v[k], v[k + 1]);
+        constexpr bool kLastPaired = (F & 1) && NMF >= 1;      // slot F = mask float of field F - 1, right next to its value
+        if constexpr (kLastPaired) fma2(swv[F - 1], sw[F - 1], w, v[F - 1], v[F]);
+        else if constexpr (F & 1) swv[F - 1] = fmaf(w, v[F - 1], swv[F - 1]);
+#pragma unroll
+        for (int s = F + (kLastPaired ? 1 : 0); s < 7; ++s) sw[2 * F - 1 - s] = fmaf(w, v[s], sw[2 * F - 1 - s]);
+        const uint32_t mb = __float_as_uint(v[7]);
+#pragma unroll
+        for (int f = 0; f < F - NMF; ++f)                      // one R2P + a predicated FADD per field
+            if (!((mb >> (f + Layout<F>::SH)) & 1u)) sw[f] = __fadd_rn(sw[f], w);
+    } else {
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+            const bool m = __float_as_uint(v[f]) == kMaskedBits;   // interpolate.py:78-79
+            if (!m) {                                              // predicated: ISETP + FADD + FFMA per field
+                sw[f] = __fadd_rn(sw[f], w);
+                swv[f] = fmaf(w, v[f], swv[f]);
+            }
         }
     }
 }
@@ -666,6 +748,44 @@ __device__ __forceinline__ void gather_run(const uint2* __restrict__ pairs, cons
         p += step;
     }
 #endif
+}
+
+// Rows far longer than a group is wide (the voxels next to the radar see the first gates of every ray: 3 600 pairs at
+// cfg1, 10 800 at cfg3 / cfg5) are cut into chunks of kHeavyChunk pairs and every chunk is reduced by a whole CTA in
+// its own small launch, ahead of the column kernel, which then only adds the chunks' partial sums (fixed chunk and
+// thread partition: deterministic).  Round 1 summed these rows with one warp inside the column kernel while the rest of
+// the patch waited: 0.33 of the roofline at cfg1, 0.09 on the lowest z-slab of cfg5.
+template <int F>
+__global__ void __launch_bounds__(kHeavyThreads) heavy_rows_kernel(const __grid_constant__ ApplyParams p)
+{
+    constexpr unsigned kFull = 0xFFFFFFFFu;
+    __shared__ float part[kHeavyThreads / 32][2 * F];
+    const uint2 ch = __ldg(p.heavy_chunks + blockIdx.x);
+    const RecSrc rec{p.records, p.records_b, p.tex_a, p.tex_b, p.null_gate};
+    float swv[F], sw[F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) { swv[f] = 0.f; sw[f] = 0.f; }
+    gather_run<F>(p.pairs, rec, ch.x + threadIdx.x, ch.x + ch.y, kHeavyThreads, swv, sw);
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            swv[f] += __shfl_xor_sync(kFull, swv[f], off);
+            sw[f] += __shfl_xor_sync(kFull, sw[f], off);
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+#pragma unroll
+        for (int f = 0; f < F; ++f) { part[warp][f] = swv[f]; part[warp][F + f] = sw[f]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * F) {
+        float t = part[0][threadIdx.x];
+#pragma unroll
+        for (int w = 1; w < kHeavyThreads / 32; ++w) t += part[w][threadIdx.x];
+        p.heavy_part[(size_t)blockIdx.x * (2 * F) + threadIdx.x] = t;
+    }
 }
 
 // PSIG: 0 = no products, 1 = any product list (op list over shared-memory state), 2 = the operational request
@@ -807,29 +927,19 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
             }
             bool heavy_mine = ce - cs > kHeavyRow;
             if constexpr (W < 32) {
-                // Rows far longer than the group is wide (the voxels next to the radar see the first gates
-                // of every ray) are summed by the whole warp, then handed back to the owning group.
-                unsigned heavy = (IL ? il_hv : __any_sync(kFull, heavy_mine)) ? __ballot_sync(kFull, heavy_mine && gl == 0) : 0u;
-                while (heavy) {
-                    const int src = __ffs(heavy) - 1;
-                    heavy &= heavy - 1;
-                    const uint32_t hs = __shfl_sync(kFull, cs, src);
-                    const uint32_t he = __shfl_sync(kFull, ce, src);
-                    float hwv[F], hw[F];
-#pragma unroll
-                    for (int f = 0; f < F; ++f) { hwv[f] = 0.f; hw[f] = 0.f; }
-                    gather_run<F>(pairs, rec, hs + lane, he, 32, hwv, hw);
-#pragma unroll
-                    for (int f = 0; f < F; ++f) {
-#pragma unroll
-                        for (int off = 16; off >= 1; off >>= 1) {
-                            hwv[f] += __shfl_xor_sync(kFull, hwv[f], off);
-                            hw[f] += __shfl_xor_sync(kFull, hw[f], off);
-                        }
+                // heavy rows were summed by heavy_rows_kernel: the group's first lane adds up the chunks' partial sums
+                if (heavy_mine && gl == 0) {
+                    const uint32_t r32 = (uint32_t)row;
+                    int lo = 0, hi = p.n_heavy - 1;
+                    while (lo < hi) {                              // sorted list of a few hundred rows at most
+                        const int mid = (lo + hi) >> 1;
+                        if (__ldg(p.heavy_rows + mid) < r32) lo = mid + 1; else hi = mid;
                     }
-                    if (lane == src) {                              // group leader keeps the row total
+                    const uint32_t c0 = __ldg(p.heavy_first + lo), c1 = __ldg(p.heavy_first + lo + 1);
+                    for (uint32_t c = c0; c < c1; ++c) {
+                        const float* hp = p.heavy_part + (size_t)c * (2 * F);
 #pragma unroll
-                        for (int f = 0; f < F; ++f) { swv[f] = hwv[f]; sw[f] = hw[f]; }
+                        for (int f = 0; f < F; ++f) { swv[f] += hp[f]; sw[f] += hp[F + f]; }
                     }
                 }
             } else {
@@ -1191,11 +1301,14 @@ struct RowTerms {
     bool weights_only;
     int stride;        // floats per gate in the array `rec` points at
     int offset;        // position of the field inside its record
+    int mask_slot;     // >= 0: slot of the record's mask-bit word (32-byte records), -1: masked values carry kMaskedBits
+    int mask_shift;    // Layout<F>::SH
     __device__ __forceinline__ float at(uint32_t i) const
     {
         const uint2 pr = __ldg(pairs + i);
         const float v = __ldg(rec + (size_t)pr.x * stride + offset);
-        const bool m = __float_as_uint(v) == kMaskedBits;
+        const bool m = mask_slot >= 0 ? (__float_as_uint(__ldg(rec + (size_t)pr.x * stride + mask_slot)) >> (field + mask_shift)) & 1u
+                                      : __float_as_uint(v) == kMaskedBits;
         const float we = m ? 0.f : __uint_as_float(pr.y);
         if (weights_only) return we;
         return __fmul_rn(we, m ? 0.f : v);                                  // interpolate.py:82
@@ -1271,9 +1384,11 @@ __global__ void __launch_bounds__(128) apply_reference_order_kernel(const __grid
         if (out == nullptr) continue;
         float v = p.fill;
         if (e > s) {
-            const int fa = p.n_fields == 1 ? 1 : p.n_fields == 2 ? 2 : 4;
-            const int fb = p.n_fields <= 4 ? 0 : p.n_fields == 5 ? 1 : p.n_fields == 6 ? 2 : 4;
-            RowTerms<FP> t{p.pairs, f < fa ? p.records : p.records_b, f, false, f < fa ? fa : fb, f < fa ? f : f - fa};
+            const bool r32 = RG_REC32 && p.n_fields >= 5;          // see Layout<F>
+            const int fa = r32 ? 8 : p.n_fields == 1 ? 1 : p.n_fields == 2 ? 2 : 4;
+            const int fb = r32 || p.n_fields <= 4 ? 0 : p.n_fields == 5 ? 1 : p.n_fields == 6 ? 2 : 4;
+            RowTerms<FP> t{p.pairs, f < fa ? p.records : p.records_b, f, false, f < fa ? fa : fb, f < fa ? f : f - fa,
+                           r32 && p.n_fields <= 7 ? 7 : -1, p.n_fields <= 6 ? 1 : 0};
             float swv = t.at(s);
             if (e - s > 1) swv = __fadd_rn(swv, pairwise_sum<FP>(t, s + 1, e - s - 1));
             t.weights_only = true;
@@ -1370,9 +1485,18 @@ static int pick_group_width(const Context* ctx, const Geometry* g, int n_fields,
     return W;
 }
 
+template <int F>
+static void launch_heavy(Context* ctx, const ApplyParams& p)
+{
+    heavy_rows_kernel<F><<<(unsigned)p.n_heavy_chunks, kHeavyThreads, 0, ctx->stream>>>(p);
+}
+
 int launch_apply(Context* ctx, const Geometry* g, const ApplyParams& p, bool reference_order)
 {
-    if (g->n_rows == 0) return RG_OK;
+    // An empty z-slab (z_begin == z_end: more ranks than levels) has no rows, but a fused products request must still
+    // get its planes: the column kernel walks zero levels and writes the initial state (NaN; 0/0 for COLMEAN).
+    const bool empty_slab = g->n_rows == 0;
+    if (empty_slab && (reference_order || !p.prod.any || g->ncol == 0)) return RG_OK;
     if (reference_order) {
         const unsigned blocks = (unsigned)((g->n_rows + 127) / 128);
         switch (records_width(p.n_fields)) {
@@ -1405,12 +1529,24 @@ int launch_apply(Context* ctx, const Geometry* g, const ApplyParams& p, bool ref
         RG_CUDA(cudaGetLastError());
         return RG_OK;
     }
-    const bool slices = use_slices(ctx, p.n_fields);
+    const bool slices = !empty_slab && use_slices(ctx, p.n_fields);
     const int W = pick_group_width(ctx, g, p.n_fields, slices);
     ApplyParams q = p;
     q.quads = nullptr;
     q.quad_ptr = nullptr;
     q.quads_x = 0;
+    q.heavy_rows = nullptr; q.heavy_first = nullptr; q.heavy_chunks = nullptr; q.heavy_part = nullptr;
+    q.n_heavy = 0; q.n_heavy_chunks = 0;
+    if (W < 32 && !empty_slab) {                        // a 32-lane group IS the whole warp: nothing is "heavy" for it
+        Geometry* gm = const_cast<Geometry*>(g);
+        RG_TRY(ensure_heavy(ctx, gm));
+        if (g->n_heavy > 0) {
+            RG_TRY(ensure(ctx, ctx->heavy, (size_t)g->n_heavy_chunks * 2 * p.n_fields * sizeof(float)));
+            q.heavy_rows = g->heavy_rows; q.heavy_first = g->heavy_first; q.heavy_chunks = g->heavy_chunks;
+            q.heavy_part = (float*)ctx->heavy.ptr;
+            q.n_heavy = (int32_t)g->n_heavy; q.n_heavy_chunks = (int32_t)g->n_heavy_chunks;
+        }
+    }
 #if RG_TILE2D && RG_HEADBATCH == 2
     if (slices) {                                       // pairs from the warp-slice copy (built on first use)
         const Geometry::QuadCopy* qc = nullptr;
@@ -1423,6 +1559,20 @@ int launch_apply(Context* ctx, const Geometry* g, const ApplyParams& p, bool ref
     }
 #endif
     timer_begin(ctx, kTimerApply);
+    if (q.n_heavy_chunks > 0) {
+        switch (q.n_fields) {
+            case 1: launch_heavy<1>(ctx, q); break;
+            case 2: launch_heavy<2>(ctx, q); break;
+            case 3: launch_heavy<3>(ctx, q); break;
+            case 4: launch_heavy<4>(ctx, q); break;
+            case 5: launch_heavy<5>(ctx, q); break;
+            case 6: launch_heavy<6>(ctx, q); break;
+            case 7: launch_heavy<7>(ctx, q); break;
+            case 8: launch_heavy<8>(ctx, q); break;
+            default: return fail(RG_ERR_INVALID, "n_fields must be 1..8");
+        }
+        ctx->launches++;
+    }
     switch (q.n_fields) {
         case 1: launch_columns_w<1>(ctx, q, W); break;
         case 2: launch_columns_w<2>(ctx, q, W); break;

@@ -548,6 +548,19 @@ __global__ void __launch_bounds__(128) quad_fill_kernel(const uint32_t* __restri
     }
 }
 
+// ---- heavy rows --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) heavy_list_kernel(const uint32_t* __restrict__ indptr, int64_t n_rows, uint32_t heavy_len,
+                                                         uint32_t capacity, uint32_t* __restrict__ rows, unsigned int* __restrict__ count)
+{
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    const uint32_t s = indptr[row], e = indptr[row + 1];
+    if (e - s > heavy_len) {
+        const unsigned int k = atomicAdd(count, 1u);
+        if (k < capacity) { rows[3 * k] = (uint32_t)row; rows[3 * k + 1] = s; rows[3 * k + 2] = e; }
+    }
+}
+
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
@@ -664,6 +677,61 @@ int ensure_quads(Context* ctx, Geometry* g, int W, const Geometry::QuadCopy** ou
     qc.n_slots = (int64_t)total;
     qc.quads_x = quads_x;
     g->info.device_bytes += (int64_t)((size_t)total * 32 * sizeof(uint2) + ((size_t)n_slices + 1) * sizeof(uint32_t));
+    return RG_OK;
+}
+
+int ensure_heavy(Context* ctx, Geometry* g)
+{
+    std::lock_guard<std::mutex> lock(g->quad_mu);
+    if (g->n_heavy >= 0) return RG_OK;
+    if (g->n_rows >= 0xFFFFFFFFll) return fail(RG_ERR_UNSUPPORTED, "more than 2^32-1 rows in one slab; use more z-slabs");
+    if (g->n_rows == 0 || (uint64_t)g->info.max_row_len <= kHeavyRow) { g->n_heavy = 0; return RG_OK; }
+    DevBuf<unsigned int> count;
+    DevBuf<uint32_t> rows;
+    RG_CUDA(count.alloc(1));
+    uint32_t capacity = 1u << 16;
+    struct Heavy { uint32_t row, s, e; };
+    std::vector<Heavy> found;
+    for (;;) {                                                   // second round only if the first list was too small
+        if (rows.p) { cudaFree(rows.p); rows.p = nullptr; }
+        RG_CUDA(rows.alloc((size_t)3 * capacity));
+        RG_CUDA(cudaMemsetAsync(count.p, 0, sizeof(unsigned int), ctx->stream));
+        heavy_list_kernel<<<(unsigned)((g->n_rows + 255) / 256), 256, 0, ctx->stream>>>(g->indptr, g->n_rows, kHeavyRow, capacity, rows.p, count.p);
+        ctx->launches++;
+        RG_CUDA(cudaGetLastError());
+        unsigned int n_found = 0;
+        RG_CUDA(cudaMemcpyAsync(&n_found, count.p, sizeof(n_found), cudaMemcpyDeviceToHost, ctx->stream));
+        RG_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (n_found <= capacity) {
+            found.resize(n_found);
+            if (n_found) RG_CUDA(cudaMemcpy(found.data(), rows.p, (size_t)n_found * sizeof(Heavy), cudaMemcpyDeviceToHost));
+            break;
+        }
+        capacity = n_found;
+    }
+    // the atomic append order is arbitrary; nothing downstream may depend on it
+    std::sort(found.begin(), found.end(), [](const Heavy& a, const Heavy& b) { return a.row < b.row; });
+    const size_t n = found.size();
+    std::vector<uint32_t> host_rows(n), ptr(2 * n);
+    for (size_t i = 0; i < n; ++i) { host_rows[i] = found[i].row; ptr[2 * i] = found[i].s; ptr[2 * i + 1] = found[i].e; }
+    std::vector<uint32_t> first(n + 1, 0);
+    std::vector<uint2> chunks;
+    for (size_t i = 0; i < n; ++i) {
+        first[i] = (uint32_t)chunks.size();
+        for (uint32_t s = ptr[2 * i]; s < ptr[2 * i + 1]; s += kHeavyChunk)
+            chunks.push_back(make_uint2(s, std::min(kHeavyChunk, ptr[2 * i + 1] - s)));
+    }
+    first[n] = (uint32_t)chunks.size();
+    if (n) {
+        RG_CUDA(cudaMalloc(&g->heavy_rows, n * sizeof(uint32_t)));
+        RG_CUDA(cudaMalloc(&g->heavy_first, (n + 1) * sizeof(uint32_t)));
+        RG_CUDA(cudaMalloc(&g->heavy_chunks, chunks.size() * sizeof(uint2)));
+        RG_CUDA(cudaMemcpy(g->heavy_rows, host_rows.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        RG_CUDA(cudaMemcpy(g->heavy_first, first.data(), (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        RG_CUDA(cudaMemcpy(g->heavy_chunks, chunks.data(), chunks.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    }
+    g->n_heavy_chunks = (int64_t)chunks.size();
+    g->n_heavy = (int64_t)n;
     return RG_OK;
 }
 

@@ -41,7 +41,9 @@ constexpr uint32_t kInvalidCell = 0xFFFFFFFFu;
 #define RG_APPLY_THREADS 128
 #endif
 constexpr int kApplyThreads = RG_APPLY_THREADS;   // threads per CTA of the column-tile apply kernel
-constexpr uint32_t kHeavyRow = 512;      // rows longer than this are reduced by the whole warp
+constexpr uint32_t kHeavyRow = 512;      // rows longer than this are reduced by whole CTAs in their own launch (heavy_rows_kernel)
+constexpr uint32_t kHeavyChunk = 4096;   // pairs of a heavy row one CTA of kHeavyThreads reduces
+constexpr int kHeavyThreads = 256;
 constexpr int kSellThreads = 64;         // threads per CTA of the thread-per-column apply kernel
 constexpr uint32_t kSellCap = 192;       // pairs of a row kept in the interleaved copy; the rest is read from the CSR
 
@@ -69,6 +71,12 @@ struct Geometry {
         int32_t quads_x = 0;
     } quad[4];
     std::mutex quad_mu;
+    // Rows longer than kHeavyRow (voxels next to the radar see the first gates of every ray): sorted row ids, the
+    // chunks (<= kHeavyChunk pairs) they are cut into, built once per table under quad_mu (ensure_heavy).
+    uint32_t* heavy_rows = nullptr;      // [n_heavy] ascending local row ids
+    uint32_t* heavy_first = nullptr;     // [n_heavy + 1] first chunk of every heavy row
+    uint2* heavy_chunks = nullptr;       // [n_heavy_chunks] {first pair, number of pairs}
+    int64_t n_heavy = -1, n_heavy_chunks = 0;   // -1: not looked for yet
     float* x_ax = nullptr;               // [nx]   float32 linspace axes (reference compute.py:184-186)
     float* y_ax = nullptr;               // [ny]
     float* z_ax = nullptr;               // [nz]   (full grid)
@@ -103,9 +111,11 @@ struct Context {
     const void* tex_a_ptr = nullptr;
     const void* tex_b_ptr = nullptr;
     int tex_fields = 0;
+    int64_t tex_gates = -1;
     Scratch stage_in;                    // H2D staging of fields / masks / rule values
     Scratch stage_out;                   // device-side outputs of a host-memspace call
     Scratch misc;
+    Scratch heavy;                       // per-chunk partial sums of the heavy rows: float[n_heavy_chunks][2 * F]
 };
 
 int ensure(Context* ctx, Scratch& s, size_t bytes);
@@ -161,6 +171,11 @@ struct ApplyParams {
     const uint32_t* quad_ptr;
     int32_t quads_x;
     uint32_t null_gate;                   // index of the all-masked record (= n_gates)
+    const uint32_t* heavy_rows;           // rows summed by heavy_rows_kernel (sorted), their chunk ranges and partial sums
+    const uint32_t* heavy_first;
+    const uint2* heavy_chunks;
+    float* heavy_part;                    // [n_heavy_chunks][2 * n_fields]: sum(w*v) per field, then sum(w) per field
+    int32_t n_heavy, n_heavy_chunks;
     unsigned long long tex_a, tex_b;      // texture objects over records / records_b (RG_TEX builds)
     int64_t ncol;                         // ny*nx
     int32_t nx, ny;
@@ -208,6 +223,7 @@ int build_geometry_device(Context* ctx, const float* gx, const float* gy, const 
 int finalize_geometry_stats(Context* ctx, Geometry* g);
 int build_sell(Context* ctx, Geometry* g);
 int ensure_quads(Context* ctx, Geometry* g, int W, const Geometry::QuadCopy** out);
+int ensure_heavy(Context* ctx, Geometry* g);
 int exclusive_scan_u32(Context* ctx, const uint32_t* in, uint32_t* out, int64_t n, unsigned long long* tmp, uint64_t* total_host);
 void linspace_f32(double start, double stop, int num, float* out);
 

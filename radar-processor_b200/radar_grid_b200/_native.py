@@ -99,6 +99,9 @@ _lib_lock = threading.Lock()
 
 
 def library_path() -> str:
+    # RADAR_GRID_B200_LIB is a DEVELOPMENT switch (A/B builds made with build.py --variant, the CPU emulator of
+    # tools/cpu_emu): it must name a build of this library and is checked against the ABI version on load; it is never
+    # set by the package, the tests' defaults, bench.py or __graft_entry__.py.
     override = os.environ.get("RADAR_GRID_B200_LIB")
     if override:
         return override

@@ -16,10 +16,20 @@ from typing import Optional, Tuple
 import numpy as np
 
 from . import _native as N
-from .engine import DeviceGeometry
+from .engine import DeviceGeometry, GeometryCache
 from .geometry import GridGeometry
 
 logger = logging.getLogger(__name__)
+
+# Tables are built once per radar and scan strategy and reused for every volume (the reference gets that from
+# save_geometry / load_geometry on disk, geometry.py:94-150): compute_grid_geometry looks the request up here first.
+# RADAR_GRID_B200_GEOMETRY_CACHE_GB=0 disables it.
+_CACHE = GeometryCache(max_bytes=int(float(os.environ.get("RADAR_GRID_B200_GEOMETRY_CACHE_GB", "48")) * (1 << 30)))
+
+
+def geometry_cache() -> GeometryCache:
+    """The module-level device cache of neighbour tables used by compute_grid_geometry."""
+    return _CACHE
 
 
 def compute_grid_geometry(gate_x, gate_y, gate_z, grid_shape: Tuple[int, int, int], grid_limits, temp_dir: str,
@@ -38,8 +48,11 @@ def compute_grid_geometry(gate_x, gate_y, gate_z, grid_shape: Tuple[int, int, in
         raise ValueError(f"temp_dir does not exist: {temp_dir}")
     if weighting not in ("barnes2", "cressman", "nearest"):
         raise ValueError(f"Unknown weighting function: {weighting}")
-    dev = DeviceGeometry.build(gate_x, gate_y, gate_z, grid_shape, grid_limits, radar_altitude=radar_altitude,
-                               min_radius=min_radius, beam_factor=beam_factor, weighting=weighting, toa=toa)
+    params = dict(radar_altitude=radar_altitude, min_radius=min_radius, beam_factor=beam_factor, weighting=weighting, toa=toa)
+    if _CACHE.max_bytes > 0 and not N.is_device_array(gate_x):
+        dev = _CACHE.get(gate_x, gate_y, gate_z, grid_shape, grid_limits, **params)
+    else:
+        dev = DeviceGeometry.build(gate_x, gate_y, gate_z, grid_shape, grid_limits, **params)
     info = dev.info
     logger.info(f"Radar altitude: {radar_altitude:.1f} m")
     logger.info(f"TOA filter: {info['n_gates_binned']:,} gates binned below {toa}m, "

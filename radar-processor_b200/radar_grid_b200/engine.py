@@ -482,9 +482,9 @@ class GeometryCache:
     @staticmethod
     def key(gate_x, gate_y, gate_z, grid_shape, grid_limits, **params) -> str:
         import hashlib
-        h = hashlib.blake2b(digest_size=16)
+        h = hashlib.sha256()                 # SHA-NI: ~1.2 GB/s, 55 ms for the 65 MB of cfg3 gate coordinates
         for a in (gate_x, gate_y, gate_z):
-            h.update(np.ascontiguousarray(np.asarray(a), dtype=np.float32).tobytes())
+            h.update(memoryview(np.ascontiguousarray(np.asarray(a).ravel(), dtype=np.float32)))
         h.update(repr((tuple(int(v) for v in grid_shape), tuple(tuple(float(v) for v in l) for l in grid_limits),
                        sorted((k, (float(v) if isinstance(v, (int, float, np.floating, np.integer)) else v)) for k, v in params.items()))).encode())
         return h.hexdigest()
@@ -505,13 +505,11 @@ class GeometryCache:
         return sum(int(g.info["device_bytes"]) for g in self._items.values())
 
     def _evict(self):
+        # dropped, not closed: a GridGeometry handed out earlier may still hold the table; it is freed with its last user
         while len(self._items) > 1 and self.bytes_held() > self.max_bytes:
-            _, old = self._items.popitem(last=False)
-            old.close()
+            self._items.popitem(last=False)
 
     def clear(self):
-        for g in self._items.values():
-            g.close()
         self._items.clear()
 
 

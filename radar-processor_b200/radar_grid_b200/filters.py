@@ -5,7 +5,8 @@ GateFilter / GridFilter / create_mask_from_filter with the reference's names and
 GateFilter stays host-side Python, as in the reference: it accumulates an OR of boolean exclude masks over
 the flattened gates.  In addition every threshold-type excluder is remembered as a *range rule*
 (field, lo, hi), which the engine can evaluate on the GPU while it packs the gate records
-(``GateFilter.fusable_rules``), so the cfg2-style RHOHV QC filter never has to exist as a host array.
+(``GateFilter.fusable_rules``; ``apply_geometry[_multi]`` do that), so the cfg2-style RHOHV QC filter never has to
+exist as a host array: the host mask of a range rule is only computed when ``gate_excluded`` is read.
 GridFilter thresholds run on the GPU (``rg_plane_filter``); only ``apply_custom`` calls back into Python.
 """
 
@@ -32,21 +33,26 @@ class GateFilter:
         self._filter_history: List[str] = []
         self._rules: List[Tuple[str, Optional[float], Optional[float]]] = []   # fusable (field, lo, hi)
         self._opaque = False            # True once a non-range excluder contributed to the mask
+        self._pending: List[Callable[[], np.ndarray]] = []   # range rules whose host mask nobody has asked for yet
 
     # ---- views
     @property
     def gate_excluded(self) -> np.ndarray:
+        # Range rules are kept as rules: apply_geometry evaluates them on the GPU (interpolate._field_inputs), so their
+        # host masks are only computed if somebody reads this attribute, as the reference's callers may.
+        while self._pending:
+            self._gate_excluded = self._gate_excluded | self._pending.pop(0)()
         return self._gate_excluded
 
     @property
     def gate_included(self) -> np.ndarray:
-        return ~self._gate_excluded
+        return ~self.gate_excluded
 
     def n_excluded(self) -> int:
-        return self._gate_excluded.sum()
+        return self.gate_excluded.sum()
 
     def n_included(self) -> int:
-        return (~self._gate_excluded).sum()
+        return (~self.gate_excluded).sum()
 
     def summary(self) -> str:
         ne, ni, n = self.n_excluded(), self.n_included(), self.n_gates
@@ -64,8 +70,11 @@ class GateFilter:
         raw = np.ma.masked_invalid(self.radar.fields[field_name]["data"])
         return np.ma.getdata(raw).ravel().astype("float32")
 
-    def _add_filter(self, mask: np.ndarray, description: str) -> "GateFilter":
-        self._gate_excluded = self._gate_excluded | mask
+    def _add_filter(self, mask, description: str) -> "GateFilter":
+        if callable(mask):
+            self._pending.append(mask)
+        else:
+            self._gate_excluded = self.gate_excluded | mask
         self._filter_history.append(description)
         return self
 
@@ -84,20 +93,23 @@ class GateFilter:
         if not self._has(field_name):
             return self
         self._rules.append((field_name, threshold, None))
-        return self._add_filter(self._get_field_data(field_name) < threshold, f"{field_name} < {threshold}")
+        return self._add_filter(lambda: self._get_field_data(field_name) < threshold, f"{field_name} < {threshold}")
 
     def exclude_above(self, field_name: str, threshold: float) -> "GateFilter":
         if not self._has(field_name):
             return self
         self._rules.append((field_name, None, threshold))
-        return self._add_filter(self._get_field_data(field_name) > threshold, f"{field_name} > {threshold}")
+        return self._add_filter(lambda: self._get_field_data(field_name) > threshold, f"{field_name} > {threshold}")
 
     def exclude_outside(self, field_name: str, low: float, high: float) -> "GateFilter":
         if not self._has(field_name):
             return self
-        v = self._get_field_data(field_name)
         self._rules.append((field_name, low, high))
-        return self._add_filter((v < low) | (v > high), f"{field_name} outside [{low}, {high}]")
+
+        def mask():
+            v = self._get_field_data(field_name)
+            return (v < low) | (v > high)
+        return self._add_filter(mask, f"{field_name} outside [{low}, {high}]")
 
     def exclude_between(self, field_name: str, low: float, high: float) -> "GateFilter":
         if not self._has(field_name):
@@ -190,6 +202,7 @@ class GateFilter:
     def copy(self) -> "GateFilter":
         other = GateFilter(self.radar)
         other._gate_excluded = self._gate_excluded.copy()
+        other._pending = list(self._pending)
         other._filter_history = self._filter_history.copy()
         other._rules = list(self._rules)
         other._opaque = self._opaque
@@ -199,6 +212,7 @@ class GateFilter:
         self._gate_excluded = np.zeros(self.n_gates, dtype=bool)
         self._filter_history = []
         self._rules = []
+        self._pending = []
         self._opaque = False
         return self
 
@@ -206,6 +220,7 @@ class GateFilter:
         return self.reset()
 
     def exclude_all(self) -> "GateFilter":
+        self._pending = []
         self._gate_excluded = np.ones(self.n_gates, dtype=bool)
         self._filter_history.append("exclude all")
         self._opaque = True

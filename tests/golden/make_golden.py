@@ -138,6 +138,83 @@ def main():
     np.savez_compressed(os.path.join(HERE, "ref_filters_tiny.npz"), **flt)
     print("ref_filters_tiny.npz:", len(flt), "arrays")
 
+    golden_multi(ref)
+    golden_cfg1(ref)
+
+
+def golden_multi(ref):
+    """apply_geometry_multi of the real reference (interpolate.py:107-142): five fields, with and without a per-field
+    filter dict (a list for one field, a bare GateFilter for another, as the reference's tests pass them)."""
+    from radar_grid_b200 import synthetic as S
+    spec = S.SPECS["small"]
+    radar = S.SyntheticRadar(spec, seed=7)
+    z = np.load(os.path.join(HERE, "ref_small_barnes2_alt0.npz"))
+    geom = ref.geometry.GridGeometry(grid_shape=spec.grid_shape, grid_limits=spec.grid_limits, indptr=z["indptr"],
+                                     gate_indices=z["gate_indices"], weights=z["weights"], toa=float(z["toa"][0]))
+    fields = {name: ref.utils.get_field_data(radar, name) for name in spec.fields}
+    gf_rho = ref.filters.GateFilter(radar).exclude_below("RHOHV", 0.8).exclude_above("RHOHV", 1.0)
+    gf_dbz = ref.filters.GateFilter(radar).exclude_below("DBZH", 5.0)
+    out = {}
+    for name, g in ref.interpolate.apply_geometry_multi(geom, fields).items():
+        out[f"plain_{name}"] = g
+    filt = {"DBZH": [gf_rho, gf_dbz], "ZDR": gf_rho}
+    for name, g in ref.interpolate.apply_geometry_multi(geom, fields, additional_filters=filt, fill_value=-5.0).items():
+        out[f"filt_{name}"] = g
+    np.savez_compressed(os.path.join(HERE, "ref_multi_small.npz"), **out)
+    print("ref_multi_small.npz:", len(out), "grids")
+
+
+def row_digest(indptr, idx, w):
+    """Order-independent description of a table: SHA-256 of the gate ids with every row sorted by gate id, and per
+    voxel column the int64 sum of the float32 bit patterns of its weights (a 1-ulp difference moves a sum by 1)."""
+    import hashlib
+    indptr = np.asarray(indptr, dtype=np.int64)
+    lens = np.diff(indptr)
+    row_of = np.repeat(np.arange(len(lens), dtype=np.int64), lens)
+    order = np.lexsort((idx, row_of))
+    sha = hashlib.sha256(np.ascontiguousarray(idx[order], dtype=np.int32).tobytes()).hexdigest()
+    return sha, row_of, lens
+
+
+def golden_cfg1(ref):
+    """BASELINE configs[0]/[1] at FULL size through the real reference: compute_grid_geometry on the cfg1 volume
+    (1.16 M voxels, 1.15e7 pairs, ~15 s on 7 workers), then apply_geometry + COLMAX (+ the cfg2 RHOHV filter, PPI 0.5
+    deg and CAPPI 4000 m).  The table itself is 100 MB, so what is committed is its digest: row lengths, the SHA-256 of
+    the row-sorted gate ids, per-column sums of the weights' bit patterns, and the 2-D products."""
+    import warnings
+    from radar_grid_b200 import synthetic as S
+    spec = S.SPECS["cfg2"]                      # the cfg1 volume + RHOHV
+    radar = S.SyntheticRadar(spec, seed=1)
+    gx, gy, gz = ref.utils.get_gate_coordinates(radar)
+    with tempfile.TemporaryDirectory() as tmp:
+        geom = ref.compute.compute_grid_geometry(gx, gy, gz, spec.grid_shape, spec.grid_limits, tmp,
+                                                 min_radius=spec.min_radius, beam_factor=spec.beam_factor,
+                                                 weighting=spec.weighting, toa=spec.toa, n_workers=max(1, (os.cpu_count() or 2) - 1))
+    nz, ny, nx = spec.grid_shape
+    sha, row_of, lens = row_digest(geom.indptr, geom.gate_indices, geom.weights)
+    col_of = row_of % (ny * nx)
+    wsum = np.bincount(col_of, weights=None, minlength=ny * nx) * 0
+    wbits = geom.weights.view(np.int32).astype(np.int64)
+    wsum = np.zeros(ny * nx, dtype=np.int64)
+    np.add.at(wsum, col_of, wbits)
+    dbz = ref.utils.get_field_data(radar, "DBZH")
+    gf = ref.filters.GateFilter(radar).exclude_below("RHOHV", 0.8).exclude_above("RHOHV", 1.0)
+    g = ref.interpolate.apply_geometry(geom, dbz)
+    gq = ref.interpolate.apply_geometry(geom, dbz, additional_filters=[gf])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = {
+            "row_len": lens.astype(np.uint16 if lens.max() < 65536 else np.uint32),
+            "gate_ids_sha256": np.array(sha), "n_pairs": np.array([geom.n_pairs()], dtype=np.int64),
+            "weight_bits_colsum": wsum,
+            "colmax": ref.products.column_max(g), "colmax_qc": ref.products.column_max(gq),
+            "cappi_4000_qc": np.array(ref.products.constant_altitude_ppi(gq, geom, 4000.0)),
+            "ppi_0.5_qc": ref.products.constant_elevation_ppi(gq, geom, 0.5),
+            "grid_nan_count": np.array([int(np.isnan(g).sum()), int(np.isnan(gq).sum())], dtype=np.int64),
+        }
+    np.savez_compressed(os.path.join(HERE, "ref_cfg1_digest.npz"), **out)
+    print(f"ref_cfg1_digest.npz: pairs={geom.n_pairs():,} max_row={lens.max()} sha={sha[:16]}")
+
 
 if __name__ == "__main__":
     main()

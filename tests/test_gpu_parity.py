@@ -451,3 +451,60 @@ def test_volume_pipeline_equals_sequential_calls():
             assert_same(a, b)
     # volumes differ from one another (the pipeline did not hand back one buffer seven times)
     assert not np.array_equal(got[0]["products"][0], got[1]["products"][0], equal_nan=True)
+
+
+def test_heavy_rows_go_through_the_chunk_kernel():
+    """Rows longer than 512 pairs (the voxels next to the radar) are reduced by heavy_rows_kernel, in chunks of 4096
+    pairs, and picked up by the column kernel: a hand-made table with rows of 600, 5 000 and 9 000 pairs next to
+    ordinary and empty rows, every field count and both table layouts, against the oracle."""
+    rng = np.random.default_rng(42)
+    shape, limits = (3, 2, 9), ((0.0, 2000.0), (-500.0, 500.0), (-2000.0, 2000.0))
+    n_gates = 12000
+    lens = rng.integers(0, 40, size=int(np.prod(shape)))
+    lens[[4, 5, 13]] = (5000, 600, 9000)            # same slice / same column (rows 4 and 13 are not; 4 and 22 would be)
+    lens[22] = 513
+    lens[[0, 30]] = 0
+    indptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    idx = np.concatenate([np.sort(rng.choice(n_gates, size=n, replace=False)) for n in lens]).astype(np.int32)
+    w = rng.uniform(0.02, 1.0, size=idx.shape[0]).astype(np.float32)
+    dev = rg.DeviceGeometry.from_csr(indptr, idx, w, shape, limits, n_gates)
+    fields = []
+    for f in range(8):
+        v = rng.normal(10.0 * f, 5.0, size=n_gates).astype(np.float32)
+        v[rng.random(n_gates) < (0.5 if f == 0 else 0.05)] = np.nan
+        fields.append(np.ma.masked_invalid(v))
+    want = [O.apply_geometry(indptr, idx, w, shape, f) for f in fields]
+    assert not np.isnan(want[0].ravel()[[4, 5, 13, 22]]).any()
+    import os, warnings
+    try:
+        for variant in (1, 4):
+            dev.ctx.set_option("apply_variant", variant)
+            for nf in (1, 2, 3, 4, 5, 6, 7, 8):
+                res = rg.grid_fields(dev, [np.ma.getdata(f) for f in fields[:nf]], masks=[np.ma.getmaskarray(f) for f in fields[:nf]],
+                                     products=[rg.ColumnMax()])
+                for f in range(nf):
+                    assert_close_same_mask(res["grids"][f], want[f], f"variant {variant} F={nf} field {f}")
+                    with warnings.catch_warnings():
+                        warnings.simplefilter("ignore", RuntimeWarning)
+                        assert_same(res["products"][0][f], np.nanmax(res["grids"][f], axis=0), "fused COLMAX")
+                exact = rg.grid_fields(dev, [np.ma.getdata(f) for f in fields[:nf]], masks=[np.ma.getmaskarray(f) for f in fields[:nf]],
+                                       reference_order=True)
+                for f in range(nf):
+                    assert_same(exact["grids"][f], want[f], f"reference order F={nf} field {f}")
+    finally:
+        dev.ctx.set_option("apply_variant", int(os.environ.get("RG_APPLY_VARIANT_TEST") or 0))
+
+
+def test_empty_zslab_still_writes_its_product_planes():
+    """z_begin == z_end (more ranks than levels): no rows, but COLMAX / CAPPI / COLMEAN planes of a fused request must be
+    the no-data planes, not whatever the output buffer held."""
+    spec, radar, gates, fields, g = golden_case("tiny")
+    dev = build(spec, gates, "barnes2", 0, z_range=(3, 3))
+    assert dev.n_rows == 0
+    name = list(fields)[0]
+    _, ny, nx = spec.grid_shape
+    outs = [np.full((1, ny, nx), 123.0, dtype=np.float32) for _ in range(3)]
+    res = rg.grid_fields(dev, [np.ma.getdata(fields[name])], masks=[np.ma.getmaskarray(fields[name])], want_grid=False,
+                         products=[rg.ColumnMax(), rg.LevelPick(2), rg.ColumnMean()], out_products=outs)
+    for p in res["products"]:
+        assert np.isnan(p).all()
