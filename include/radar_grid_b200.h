@@ -117,6 +117,16 @@ int rg_geometry_build(rg_context* ctx,
                       double min_radius, double beam_factor, int32_t weighting, double toa,
                       rg_geometry** out);
 
+/* Level census for balanced z-slabs (no reference counterpart; the reference's only parallelism is a Pool over z-levels,
+ * compute.py:203-222): the binning pass and the counting pass of rg_geometry_build over every `column_stride`-th
+ * column in x and y; pairs_per_level (host, z_end - z_begin entries) receives the pair count of every level, scaled
+ * to the full plane (exact for column_stride = 1).  Nothing is kept on the device. */
+int rg_geometry_level_pairs(rg_context* ctx,
+                            const float* gate_x, const float* gate_y, const float* gate_z, int64_t n_gates,
+                            int32_t memspace, const rg_grid_spec* grid, double radar_altitude,
+                            double min_radius, double beam_factor, double toa, int32_t column_stride,
+                            int64_t* pairs_per_level);
+
 /* Import an existing table (e.g. one the reference built and saved with save_geometry, reference
  * geometry.py:94-118).  indptr has n_rows+1 entries of `indptr_bits` (32 or 64) bits; row order is kept. */
 int rg_geometry_from_csr(rg_context* ctx, const rg_grid_spec* grid, const void* indptr, int32_t indptr_bits,
@@ -152,7 +162,11 @@ typedef struct rg_product {
     int32_t mode;              /* rg_blend_mode (LEVEL); for BEAM: 0 = 'linear', 1 = 'nearest' */
     int32_t z_lo, z_hi;
     int32_t earth_curvature;   /* BEAM */
-    int32_t reserved_;
+    int32_t partial;           /* 0: the finished product.  1: this z-slab's TERM of it, to be combined across slabs by one
+                                * all-reduce: COLMAX / COLMIN write -inf / +inf where the slab has no data (all-reduce MAX /
+                                * MIN); LEVEL and BEAM write the sum over the levels the slab OWNS of weight * value, -0.0
+                                * for levels of other slabs (all-reduce SUM; a float64 blend stays float64: RG_BLEND_F64
+                                * then has a float64 plane), NaN where the reference's result is NaN for every slab */
     double w_lo, w_hi;         /* LEVEL blend weights */
     double sin_elev;           /* BEAM: np.sin(np.radians(elev)) */
     double cos_elev_clamped;   /* BEAM: np.maximum(np.cos(np.radians(elev)), 0.01) */

@@ -175,6 +175,8 @@ int make_product_params(const rg_grid_spec& gs, int n_products, const rg_product
 {
     memset(pp, 0, sizeof(*pp));
     pp->nz_full = gs.nz;
+    pp->own_z0 = gs.z_begin;
+    pp->own_z1 = gs.z_end;
     pp->z_min = gs.z_min;
     pp->z_max = gs.z_max;
     // products.py:256,276: (z_max - z_min) / (nz - 1) if nz > 1 else 1.0
@@ -193,11 +195,13 @@ int make_product_params(const rg_grid_spec& gs, int n_products, const rg_product
             case RG_PROD_COLMAX:
                 if (pp->cmax_on) return fail(RG_ERR_UNSUPPORTED, "at most one COLMAX per call");
                 pp->cmax_on = 1; pp->cmax_z0 = z0; pp->cmax_z1 = z1; pp->cmax_out = (float*)out;
+                pp->cmax_partial = pr.partial != 0;
                 lo = std::min(lo, z0); hi = std::max(hi, z1);
                 break;
             case RG_PROD_COLMIN:
                 if (pp->cmin_on) return fail(RG_ERR_UNSUPPORTED, "at most one COLMIN per call");
                 pp->cmin_on = 1; pp->cmin_z0 = z0; pp->cmin_z1 = z1; pp->cmin_out = (float*)out;
+                pp->cmin_partial = pr.partial != 0;
                 lo = std::min(lo, z0); hi = std::max(hi, z1);
                 break;
             case RG_PROD_COLMEAN:
@@ -211,6 +215,7 @@ int make_product_params(const rg_grid_spec& gs, int n_products, const rg_product
                 SliceParams& s = pp->slices[pp->n_slices++];
                 s.kind = pr.kind;
                 s.mode = pr.mode;
+                s.partial = pr.partial != 0;
                 s.out = out;
                 if (pr.kind == RG_PROD_LEVEL) {
                     if (pr.mode < RG_BLEND_PICK || pr.mode > RG_BLEND_F64_OUT64) return fail(RG_ERR_INVALID, "bad blend mode");
@@ -263,7 +268,8 @@ int make_product_params(const rg_grid_spec& gs, int n_products, const rg_product
 
 size_t product_plane_bytes(const rg_product& pr, int n_fields, int64_t ncol)
 {
-    const bool f64 = (pr.kind == RG_PROD_BEAM && pr.mode == 0) || (pr.kind == RG_PROD_LEVEL && pr.mode == RG_BLEND_F64_OUT64);
+    const bool f64 = (pr.kind == RG_PROD_BEAM && pr.mode == 0) || (pr.kind == RG_PROD_LEVEL && pr.mode == RG_BLEND_F64_OUT64) ||
+                     (pr.kind == RG_PROD_LEVEL && pr.mode == RG_BLEND_F64 && pr.partial);
     return (size_t)n_fields * (size_t)ncol * (f64 ? 8 : 4);
 }
 
@@ -486,6 +492,43 @@ int rg_geometry_build(rg_context* c, const float* gate_x, const float* gate_y, c
     if (st != RG_OK) { free_geometry(g); return st; }
     *out = reinterpret_cast<rg_geometry*>(g);
     return RG_OK;
+}
+
+int rg_geometry_level_pairs(rg_context* c, const float* gate_x, const float* gate_y, const float* gate_z, int64_t n_gates,
+                            int32_t memspace, const rg_grid_spec* grid, double radar_altitude, double min_radius,
+                            double beam_factor, double toa, int32_t column_stride, int64_t* pairs_per_level)
+{
+    Context* ctx = reinterpret_cast<Context*>(c);
+    RG_ENTER(ctx);
+    RG_TRY(check_grid(grid));
+    if (!pairs_per_level) return fail(RG_ERR_INVALID, "pairs_per_level is NULL");
+    if (column_stride < 1) return fail(RG_ERR_INVALID, "column_stride must be >= 1");
+    if (n_gates < 0 || n_gates >= 0xFFFFFFFFll) return fail(RG_ERR_INVALID, "n_gates out of range");
+    if (n_gates > 0 && (!gate_x || !gate_y || !gate_z)) return fail(RG_ERR_INVALID, "gate coordinate pointer is NULL");
+    if (memspace != RG_DEVICE && memspace != RG_HOST) return fail(RG_ERR_INVALID, "bad memspace");
+    if (!(min_radius >= 0.0) || !(beam_factor >= 0.0) || !isfinite(min_radius) || !isfinite(beam_factor))
+        return fail(RG_ERR_INVALID, "min_radius and beam_factor must be finite and >= 0");
+    const float *dx = gate_x, *dy = gate_y, *dz = gate_z;
+    float* staged = nullptr;
+    if (memspace == RG_HOST && n_gates > 0) {
+        RG_CUDA(cudaMalloc(&staged, (size_t)n_gates * 3 * sizeof(float)));
+        const size_t nb = (size_t)n_gates * sizeof(float);
+        cudaError_t e = cudaMemcpyAsync(staged, gate_x, nb, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(staged + n_gates, gate_y, nb, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(staged + 2 * n_gates, gate_z, nb, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) { cudaFree(staged); return fail(RG_ERR_CUDA, cudaGetErrorString(e)); }
+        dx = staged; dy = staged + n_gates; dz = staged + 2 * n_gates;
+    }
+    Geometry* g = new (std::nothrow) Geometry();
+    if (!g) { cudaFree(staged); return fail(RG_ERR_NOMEM, "out of host memory"); }
+    g->device = ctx->device;
+    g->grid = *grid;
+    const int st = build_geometry_device(ctx, dx, dy, dz, n_gates, radar_altitude, min_radius, beam_factor, RG_W_NEAREST, toa, g,
+                                         column_stride, pairs_per_level);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(staged);
+    free_geometry(g);
+    return st;
 }
 
 int rg_geometry_from_csr(rg_context* c, const rg_grid_spec* grid, const void* indptr, int32_t indptr_bits,

@@ -48,48 +48,30 @@ namespace rg {
 #define RG_TEX 0               // 1: gather the gate records through the texture path (tex1Dfetch) instead of LDG
 #endif
 
-#ifndef RG_REC32
-#define RG_REC32 1
-#endif
-
-#if RG_TEX && RG_REC32
-#error "the texture path fetches at most 16 bytes per texel: build RG_TEX variants with -DRG_REC32=0"
+#ifndef RG_MASKBITS
+#define RG_MASKBITS 1          // 1: odd field counts keep a mask-bit word in the free record slot (see Layout); 0: marker values only
 #endif
 
 // ------------------------------------------------------------------------------------------------------
 // K4  pack: gate masks (field mask | masked_invalid | fused QC range rules) + AoS records
 // ------------------------------------------------------------------------------------------------------
-// Record layout per field count F (shared by K4, K5 and the exact kernel):
-//   F <= 4   one array A of FA = 1, 2 or 4 floats per gate; a masked value is the bit pattern kMaskedBits.
-//   F >= 5   RG_REC32 (default): ONE 32-byte record per gate, fetched with a single 256-bit load (LDG.E.256, new on
-//            sm_100): slots [0, F) hold the values with masked values stored as +0.0, slot 7 holds one mask bit per
-//            field (bit f set = field f masked) and the slots between carry the masks of the highest-numbered fields
-//            as floats (1.0 = valid, 0.0 = masked; F = 5: slot 5 = field 4, slot 6 = field 3; F = 6: slot 6 = field 5).
-//            Sums of w*v then need no predicate and pair up into packed FFMA2s, a mask float turns sum(w) into one
-//            more FFMA(2) lane, and the remaining fields take their predicates from the mask word with one R2P.
-//            F = 8 has no room for the mask word and keeps the marker scheme.
-//            Without RG_REC32: arrays A = float[G+1][4] and B = float[G+1][FB] (the round-1 layout, kept for A/B runs).
+// Record layout per field count F (shared by K4, K5 and the exact kernel): array A = float[G+1][FA] holds fields 0..3,
+// array B = float[G+1][FB] fields 4..7 (an interleaved 32-byte record lost twice: as two 128-bit loads in round 1 and
+// as one 256-bit load, LDG.E.256, in round 2 -- 0.855 vs 0.643 ms).
+//   MB layouts (odd F >= 3: one float of the last vector is free): masked values are stored as +0.0 and the free slot,
+//   v[F], holds one mask bit per field (bit f + SH set = field f masked).  sum(w*v) then needs no predicate and pairs
+//   up into packed FFMA2s (fma.rn.f32x2, sm_100+), and the predicates of the sum(w) adds come out of the mask word
+//   with ONE R2P instead of an ISETP per field: 9 instead of 15 instructions per pair at five fields.
+//   Other F: a masked value is the bit pattern kMaskedBits (ISETP + predicated FADD + FFMA per field).
 template <int F>
 struct Layout {
-    static constexpr bool R32 = RG_REC32 && F >= 5;
     static constexpr int FP = F == 1 ? 1 : F == 2 ? 2 : F <= 4 ? 4 : 8;
-    static constexpr int FA = R32 ? 8 : F == 1 ? 1 : F == 2 ? 2 : 4;
-    static constexpr int FB = R32 || F <= 4 ? 0 : F == 5 ? 1 : F == 6 ? 2 : 4;
+    static constexpr int FA = F == 1 ? 1 : F == 2 ? 2 : 4;
+    static constexpr int FB = F <= 4 ? 0 : F <= 6 ? 2 : 4;
     static constexpr int NV = FA + FB;           // floats gathered per gate
-    static constexpr bool MB = R32 && F <= 7;    // mask bits in slot 7, masked values stored as 0
-    static constexpr int NMF = MB ? 7 - F : 0;   // mask floats in slots [F, 7): slot s belongs to field 2F - 1 - s
-    static constexpr int SH = F <= 6 ? 1 : 0;    // field f's mask bit is bit f + SH: R2P fills P1.. in one instruction, bit 0 costs two more
+    static constexpr bool MB = RG_MASKBITS && (F == 3 || F == 5 || F == 7);   // mask bits in slot F = NV - 1
+    static constexpr int SH = F <= 5 ? 1 : 0;    // R2P fills P1.. in one instruction; bit 0 would cost two more
 };
-
-__device__ __forceinline__ void store_vec8(float* dst, const float* v)
-{
-#ifndef RG_EMU
-    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
-                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
-#else
-    for (int i = 0; i < 8; ++i) dst[i] = v[i];
-#endif
-}
 
 template <int F>
 __global__ void __launch_bounds__(256) pack_records_kernel(const __grid_constant__ PackParams p)
@@ -128,17 +110,12 @@ __global__ void __launch_bounds__(256) pack_records_kernel(const __grid_constant
             out[f] = __uint_as_float(bits);
         }
     }
-    if constexpr (L::MB) {
-#pragma unroll
-        for (int s = F; s < 7; ++s) out[s] = (mask_bits >> (2 * F - 1 - s + L::SH)) & 1u ? 0.f : 1.f;
-        out[7] = __uint_as_float(mask_bits);
-    }
+    if constexpr (L::MB) out[F] = __uint_as_float(mask_bits);
     auto store = [](float* dst, const float* v, auto n) {
         constexpr int N = decltype(n)::value;
         if constexpr (N == 1) dst[0] = v[0];
         else if constexpr (N == 2) *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
-        else if constexpr (N == 4) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-        else store_vec8(dst, v);
+        else *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
     };
     store(p.records + (size_t)g * FA, out, std::integral_constant<int, FA>{});
     if constexpr (FB > 0) store(p.records_b + (size_t)g * FB, out + FA, std::integral_constant<int, FB>{});
@@ -152,7 +129,7 @@ int bind_record_textures(Context* ctx, const float* rec_a, const float* rec_b, i
     if (ctx->tex_a) { cudaDestroyTextureObject(ctx->tex_a); ctx->tex_a = 0; }
     if (ctx->tex_b) { cudaDestroyTextureObject(ctx->tex_b); ctx->tex_b = 0; }
     const int fa = n_fields == 1 ? 1 : n_fields == 2 ? 2 : 4;
-    const int fb = n_fields <= 4 ? 0 : n_fields == 5 ? 1 : n_fields == 6 ? 2 : 4;
+    const int fb = n_fields <= 4 ? 0 : n_fields <= 6 ? 2 : 4;
     auto make = [&](const float* ptr, int nf, unsigned long long* out) -> int {
         cudaResourceDesc rd{};
         rd.resType = cudaResourceTypeLinear;
@@ -179,7 +156,7 @@ int records_width(int n_fields) { return n_fields <= 1 ? 1 : n_fields == 2 ? 2 :
 
 size_t records_b_offset(int n_fields, int64_t n_gates)
 {
-    const int fa = RG_REC32 && n_fields >= 5 ? 8 : n_fields == 1 ? 1 : n_fields == 2 ? 2 : 4;
+    const int fa = n_fields == 1 ? 1 : n_fields == 2 ? 2 : 4;
     return (((size_t)(n_gates + 1) * fa * sizeof(float)) + 511) & ~(size_t)511;   // texture-bindable
 }
 
@@ -382,8 +359,10 @@ struct ColumnState {
     {
         const size_t o = (size_t)field * (size_t)ncol + (size_t)col;
         const float qnan = __uint_as_float(kCanonNaN);
-        if (pp.cmax_on) pp.cmax_out[o] = cmax;
-        if (pp.cmin_on) pp.cmin_out[o] = cmin;
+        // partial (z-slab) planes carry "no data in this slab" as the neutral element of the collective that follows:
+        // -inf / +inf for all-reduce(MAX / MIN), -0.0 for all-reduce(SUM) (x + -0.0 == x for every x, signed zeros included)
+        if (pp.cmax_on) pp.cmax_out[o] = pp.cmax_partial && isnan(cmax) ? __uint_as_float(0xFF800000u) : cmax;
+        if (pp.cmin_on) pp.cmin_out[o] = pp.cmin_partial && isnan(cmin) ? __uint_as_float(0x7F800000u) : cmin;
         if (pp.cmean_on) {
             // _divide_by_count: true_divide(float32 sum, intp count) evaluates in float64, stored as float32
             pp.cmean_out[o] = (float)__ddiv_rn((double)msum, (double)mcnt);
@@ -392,28 +371,37 @@ struct ColumnState {
         for (int k = 0; k < RG_MAX_SLICES; ++k) {
             if (k < pp.n_slices) {
                 const SliceParams& s = pp.slices[k];
+                const int lo = zz[k] & 0xFFFF, hi = zz[k] >> 16;
+                const bool own_lo = !s.partial || (lo >= pp.own_z0 && lo < pp.own_z1);
+                const bool own_hi = !s.partial || (hi >= pp.own_z0 && hi < pp.own_z1);
                 if (s.kind == RG_PROD_BEAM) {
                     const double tz = beam_target_z(s, x, y);
                     const double zf = __ddiv_rn(__dsub_rn(tz, pp.z_min), pp.z_step);
                     if (s.mode == 1) {
                         const double zi = rint(zf);
                         const bool ok = zi >= 0.0 && zi < (double)pp.nz_full;
-                        reinterpret_cast<float*>(s.out)[o] = ok ? s_lo[k] : qnan;       // products.py:263-272
+                        reinterpret_cast<float*>(s.out)[o] = !ok ? qnan : own_lo ? s_lo[k] : -0.0f;   // products.py:263-272
                     } else {
                         const double w_hi = __dsub_rn(zf, floor(zf));                      // products.py:287-288
                         const double w_lo = __dsub_rn(1.0, w_hi);
-                        double r = __dadd_rn(__dmul_rn(w_lo, (double)s_lo[k]), __dmul_rn(w_hi, (double)s_hi[k]));
+                        const double t_lo = own_lo ? __dmul_rn(w_lo, (double)s_lo[k]) : -0.0;
+                        const double t_hi = own_hi ? __dmul_rn(w_hi, (double)s_hi[k]) : -0.0;
+                        double r = __dadd_rn(t_lo, t_hi);
                         if (tz < pp.z_min || tz > pp.z_max) r = (double)qnan;              // products.py:306-309
                         reinterpret_cast<double*>(s.out)[o] = r;
                     }
                 } else if (s.mode == RG_BLEND_PICK) {
-                    reinterpret_cast<float*>(s.out)[o] = s_lo[k];
+                    reinterpret_cast<float*>(s.out)[o] = own_lo ? s_lo[k] : -0.0f;
                 } else if (s.mode == RG_BLEND_F32) {
-                    reinterpret_cast<float*>(s.out)[o] =
-                        __fadd_rn(__fmul_rn((float)s.w_lo, s_lo[k]), __fmul_rn((float)s.w_hi, s_hi[k]));
+                    const float t_lo = own_lo ? __fmul_rn((float)s.w_lo, s_lo[k]) : -0.0f;
+                    const float t_hi = own_hi ? __fmul_rn((float)s.w_hi, s_hi[k]) : -0.0f;
+                    reinterpret_cast<float*>(s.out)[o] = __fadd_rn(t_lo, t_hi);
                 } else {
-                    const double r = __dadd_rn(__dmul_rn(s.w_lo, (double)s_lo[k]), __dmul_rn(s.w_hi, (double)s_hi[k]));
-                    if (s.mode == RG_BLEND_F64_OUT64) reinterpret_cast<double*>(s.out)[o] = r;
+                    const double t_lo = own_lo ? __dmul_rn(s.w_lo, (double)s_lo[k]) : -0.0;
+                    const double t_hi = own_hi ? __dmul_rn(s.w_hi, (double)s_hi[k]) : -0.0;
+                    const double r = __dadd_rn(t_lo, t_hi);
+                    // a partial float64 blend stays float64 until the ranks' terms have been added
+                    if (s.mode == RG_BLEND_F64_OUT64 || s.partial) reinterpret_cast<double*>(s.out)[o] = r;
                     else reinterpret_cast<float*>(s.out)[o] = (float)r;
                 }
             }
@@ -599,15 +587,6 @@ __device__ __forceinline__ void load_vec(const float* __restrict__ base, uint32_
     } else if constexpr (N == 4) {
         const float4 t = __ldg(reinterpret_cast<const float4*>(base) + gate);
         v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-    } else if constexpr (N == 8) {
-#ifndef RG_EMU
-        // one 256-bit load (LDG.E.256, sm_100+): the whole 32-byte record of a gate in a single L1 request
-        asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-            : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
-            : "l"(base + 8 * (size_t)gate));
-#else
-        for (int i = 0; i < 8; ++i) v[i] = base[8 * (size_t)gate + i];
-#endif
     }
 }
 
@@ -666,19 +645,14 @@ template <int F, int NV>
 __device__ __forceinline__ void accumulate(float w, const float (&v)[NV], float (&swv)[F], float (&sw)[F])
 {
     if constexpr (Layout<F>::MB) {
-        // 32-byte record: masked values are +0.0, so sum(w*v) needs no predicate (interpolate.py:78-82: masked gates
-        // contribute 0 to both sums).  Bit-identical to the predicated form: x + w*0 = x, fma(w, 1, x) = x + w.
-        constexpr int NMF = Layout<F>::NMF;
+        // masked values are +0.0, so sum(w*v) needs no predicate (interpolate.py:78-82: masked gates contribute 0 to both
+        // sums).  Bit-identical to the predicated form: x + w*0 = x.
 #pragma unroll
         for (int k = 0; k + 1 < F; k += 2) fma2(swv[k], swv[k + 1], w, v[k], v[k + 1]);
-        constexpr bool kLastPaired = (F & 1) && NMF >= 1;      // slot F = mask float of field F - 1, right next to its value
-        if constexpr (kLastPaired) fma2(swv[F - 1], sw[F - 1], w, v[F - 1], v[F]);
-        else if constexpr (F & 1) swv[F - 1] = fmaf(w, v[F - 1], swv[F - 1]);
+        swv[F - 1] = fmaf(w, v[F - 1], swv[F - 1]);
+        const uint32_t mb = __float_as_uint(v[F]);
 #pragma unroll
-        for (int s = F + (kLastPaired ? 1 : 0); s < 7; ++s) sw[2 * F - 1 - s] = fmaf(w, v[s], sw[2 * F - 1 - s]);
-        const uint32_t mb = __float_as_uint(v[7]);
-#pragma unroll
-        for (int f = 0; f < F - NMF; ++f)                      // one R2P + a predicated FADD per field
+        for (int f = 0; f < F; ++f)                            // one R2P + a predicated FADD per field
             if (!((mb >> (f + Layout<F>::SH)) & 1u)) sw[f] = __fadd_rn(sw[f], w);
     } else {
 #pragma unroll
@@ -1301,14 +1275,17 @@ struct RowTerms {
     bool weights_only;
     int stride;        // floats per gate in the array `rec` points at
     int offset;        // position of the field inside its record
-    int mask_slot;     // >= 0: slot of the record's mask-bit word (32-byte records), -1: masked values carry kMaskedBits
+    const float* mask_rec;   // array holding the mask-bit word (MB layouts), nullptr: masked values carry kMaskedBits
+    int mask_stride;
+    int mask_slot;
     int mask_shift;    // Layout<F>::SH
     __device__ __forceinline__ float at(uint32_t i) const
     {
         const uint2 pr = __ldg(pairs + i);
         const float v = __ldg(rec + (size_t)pr.x * stride + offset);
-        const bool m = mask_slot >= 0 ? (__float_as_uint(__ldg(rec + (size_t)pr.x * stride + mask_slot)) >> (field + mask_shift)) & 1u
-                                      : __float_as_uint(v) == kMaskedBits;
+        const bool m = mask_rec != nullptr
+                           ? (__float_as_uint(__ldg(mask_rec + (size_t)pr.x * mask_stride + mask_slot)) >> (field + mask_shift)) & 1u
+                           : __float_as_uint(v) == kMaskedBits;
         const float we = m ? 0.f : __uint_as_float(pr.y);
         if (weights_only) return we;
         return __fmul_rn(we, m ? 0.f : v);                                  // interpolate.py:82
@@ -1384,11 +1361,13 @@ __global__ void __launch_bounds__(128) apply_reference_order_kernel(const __grid
         if (out == nullptr) continue;
         float v = p.fill;
         if (e > s) {
-            const bool r32 = RG_REC32 && p.n_fields >= 5;          // see Layout<F>
-            const int fa = r32 ? 8 : p.n_fields == 1 ? 1 : p.n_fields == 2 ? 2 : 4;
-            const int fb = r32 || p.n_fields <= 4 ? 0 : p.n_fields == 5 ? 1 : p.n_fields == 6 ? 2 : 4;
+            const int nf = p.n_fields;                             // see Layout<F>
+            const int fa = nf == 1 ? 1 : nf == 2 ? 2 : 4;
+            const int fb = nf <= 4 ? 0 : nf <= 6 ? 2 : 4;
+            const bool mb = RG_MASKBITS && (nf == 3 || nf == 5 || nf == 7);   // mask word in slot nf: A[3], B[1] or B[3]
             RowTerms<FP> t{p.pairs, f < fa ? p.records : p.records_b, f, false, f < fa ? fa : fb, f < fa ? f : f - fa,
-                           r32 && p.n_fields <= 7 ? 7 : -1, p.n_fields <= 6 ? 1 : 0};
+                           mb ? (nf == 3 ? p.records : p.records_b) : nullptr, nf == 3 ? fa : fb, mb ? (nf == 3 ? 3 : nf - fa) : -1,
+                           nf <= 5 ? 1 : 0};
             float swv = t.at(s);
             if (e - s > 1) swv = __fadd_rn(swv, pairwise_sum<FP>(t, s + 1, e - s - 1));
             t.weights_only = true;

@@ -263,6 +263,10 @@ struct NeighbourParams {
     double min_radius, beam_factor;
     int32_t weighting;
     uint32_t* counts;                     // K2 output
+    // K2 in level-census mode (rg_geometry_level_pairs): every `col_stride`-th column in x and y is counted and the
+    // counts are added up per level instead of being stored per row
+    unsigned long long* level_pairs;      // [n_levels] or nullptr
+    int32_t col_stride, nxs, nys;
     const uint32_t* indptr;               // K3 input
     uint2* pairs;                         // K3 output
     unsigned long long* n_candidates;
@@ -291,9 +295,19 @@ __global__ void __launch_bounds__(256) neighbour_kernel(const __grid_constant__ 
     unsigned long long tested = 0;
 
     if (row < p.n_rows) {
-        const int lz = (int)(row / p.ncol);
-        const int64_t c = row - (int64_t)lz * p.ncol;
-        const int iy = (int)(c / p.nx), ix = (int)(c - (int64_t)iy * p.nx);
+        int lz, iy, ix;
+        if (!FILL && p.level_pairs != nullptr) {
+            const int64_t per_level = (int64_t)p.nxs * p.nys;
+            lz = (int)(row / per_level);
+            const int64_t c = row - (int64_t)lz * per_level;
+            iy = (int)(c / p.nxs) * p.col_stride;
+            ix = (int)(c % p.nxs) * p.col_stride;
+        } else {
+            lz = (int)(row / p.ncol);
+            const int64_t c = row - (int64_t)lz * p.ncol;
+            iy = (int)(c / p.nx);
+            ix = (int)(c - (int64_t)iy * p.nx);
+        }
         // compute.py:43,189-190: float32 axis values widened to float64
         const double vx = (double)__ldg(p.x_ax + ix);
         const double vy = (double)__ldg(p.y_ax + iy);
@@ -373,7 +387,10 @@ __global__ void __launch_bounds__(256) neighbour_kernel(const __grid_constant__ 
             const uint32_t smax = __reduce_max_sync(kFull, slen);
             for (uint32_t j = 0; j < smax; ++j) test_candidate(j < slen, s + j);
         }
-        if (!FILL && lane == 0) p.counts[row] = found;
+        if (!FILL && lane == 0) {
+            if (p.level_pairs != nullptr) { if (found) atomicAdd(p.level_pairs + lz, (unsigned long long)found); }
+            else p.counts[row] = found;
+        }
     }
 
     if (!FILL) {
@@ -756,7 +773,7 @@ int finalize_geometry_stats(Context* ctx, Geometry* g)
 
 int build_geometry_device(Context* ctx, const float* gx, const float* gy, const float* gz, int64_t n_gates,
                           double radar_altitude, double min_radius, double beam_factor, int weighting, double toa,
-                          Geometry* out)
+                          Geometry* out, int col_stride, int64_t* level_pairs_host)
 {
     const rg_grid_spec& gs = out->grid;
     const int n_levels = gs.z_end - gs.z_begin;
@@ -856,6 +873,35 @@ int build_geometry_device(Context* ctx, const float* gx, const float* gy, const 
     RG_CUDA(cudaMemcpyAsync(out->y_ax, ya.data(), gs.ny * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     RG_CUDA(cudaMemcpyAsync(out->z_ax, za.data(), gs.nz * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     RG_CUDA(cudaStreamSynchronize(ctx->stream));   // xa/ya/za are stack-owned
+
+    if (level_pairs_host != nullptr) {
+        // level census: K2 over every col_stride-th column, pairs added up per level and scaled to the full plane
+        const int st = std::max(1, col_stride);
+        const int nxs = (gs.nx + st - 1) / st, nys = (gs.ny + st - 1) / st;
+        DevBuf<unsigned long long> per_level;
+        RG_CUDA(per_level.alloc((size_t)std::max(1, n_levels)));
+        RG_CUDA(cudaMemsetAsync(per_level.p, 0, (size_t)std::max(1, n_levels) * sizeof(unsigned long long), ctx->stream));
+        NeighbourParams cp{};
+        cp.sorted = sorted.p; cp.cell_start = cell_start.p; cp.cg = cg;
+        cp.x_ax = out->x_ax; cp.y_ax = out->y_ax; cp.z_ax = out->z_ax;
+        cp.nx = gs.nx; cp.ny = gs.ny; cp.z_begin = gs.z_begin; cp.ncol = ncol;
+        cp.n_rows = (int64_t)n_levels * nxs * nys;
+        cp.min_radius = min_radius; cp.beam_factor = beam_factor; cp.weighting = weighting;
+        cp.level_pairs = per_level.p; cp.col_stride = st; cp.nxs = nxs; cp.nys = nys;
+        cp.n_candidates = counters.p + 1;
+        if (cp.n_rows > 0) {
+            neighbour_kernel<false><<<(unsigned)((cp.n_rows + 7) / 8), 256, 0, ctx->stream>>>(cp);
+            ctx->launches++;
+            RG_CUDA(cudaGetLastError());
+        }
+        std::vector<unsigned long long> h(std::max(1, n_levels));
+        RG_CUDA(cudaMemcpyAsync(h.data(), per_level.p, (size_t)std::max(1, n_levels) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        RG_CUDA(cudaStreamSynchronize(ctx->stream));
+        const double scale = (double)ncol / (double)std::max<int64_t>(1, (int64_t)nxs * nys);
+        for (int l = 0; l < n_levels; ++l) level_pairs_host[l] = (int64_t)llround((double)h[l] * scale);
+        cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+        return RG_OK;
+    }
 
     // ---- K2 count
     DevBuf<uint32_t> counts;

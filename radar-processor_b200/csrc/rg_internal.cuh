@@ -128,7 +128,7 @@ struct SliceParams {                      // one RG_PROD_LEVEL / RG_PROD_BEAM pr
     int32_t mode;                         // LEVEL: rg_blend_mode.  BEAM: 0 linear, 1 nearest
     int32_t z_lo, z_hi;
     int32_t curvature;
-    int32_t pad_;
+    int32_t partial;                      // z-slab term: only the levels this slab owns contribute, the others add -0.0
     double w_lo, w_hi;
     double sin_e, cos_c, tan_e, ke_re, ke_re_sq;
     void* out;
@@ -142,6 +142,8 @@ struct ProductParams {
     uint32_t cmax_w, cmin_w, cmean_w;     // z1 - z0 + 1 when on, 0 when off
     int32_t n_slices;
     int32_t nz_full;
+    int32_t own_z0, own_z1;               // global levels [own_z0, own_z1) of the slab being gridded (partial products)
+    int32_t cmax_partial, cmin_partial;   // no-data pixels are written as -inf / +inf, ready for all-reduce(MAX / MIN)
     float* cmax_out;
     float* cmin_out;
     float* cmean_out;
@@ -219,7 +221,7 @@ int launch_products(Context* ctx, const rg_grid_spec& grid, int n_fields, const 
                     const ProductParams& prod);
 int build_geometry_device(Context* ctx, const float* gx, const float* gy, const float* gz, int64_t n_gates,
                           double radar_altitude, double min_radius, double beam_factor, int weighting,
-                          double toa, Geometry* out);
+                          double toa, Geometry* out, int col_stride = 1, int64_t* level_pairs_host = nullptr);
 int finalize_geometry_stats(Context* ctx, Geometry* g);
 int build_sell(Context* ctx, Geometry* g);
 int ensure_quads(Context* ctx, Geometry* g, int W, const Geometry::QuadCopy** out);

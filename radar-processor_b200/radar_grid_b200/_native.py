@@ -42,7 +42,7 @@ class GeometryInfo(C.Structure):
 
 class Product(C.Structure):
     _fields_ = [("kind", C.c_int32), ("mode", C.c_int32), ("z_lo", C.c_int32), ("z_hi", C.c_int32),
-                ("earth_curvature", C.c_int32), ("reserved_", C.c_int32),
+                ("earth_curvature", C.c_int32), ("partial", C.c_int32),
                 ("w_lo", C.c_double), ("w_hi", C.c_double), ("sin_elev", C.c_double),
                 ("cos_elev_clamped", C.c_double), ("tan_elev", C.c_double), ("ke_re", C.c_double),
                 ("ke_re_sq", C.c_double), ("out", C.c_void_p)]
@@ -87,6 +87,9 @@ _PROTOTYPES = {
     "rg_geometry_export_csr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                          C.c_int32]),
     "rg_geometry_destroy": (C.c_int, [C.c_void_p]),
+    "rg_geometry_level_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                          C.POINTER(GridSpec), C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32,
+                                          C.POINTER(C.c_int64)]),
     "rg_products": (C.c_int, [C.c_void_p, C.POINTER(GridSpec), C.c_int32, C.POINTER(C.c_void_p), C.c_int32,
                               C.POINTER(Product), C.c_int32]),
     "rg_plane_filter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,

@@ -35,16 +35,51 @@ def shard_volumes(n_volumes: int, world_size: int, rank: int) -> List[int]:
     return list(range(rank, n_volumes, world_size))
 
 
-def zslab_ranges(nz: int, world_size: int) -> List[Tuple[int, int]]:
-    """Contiguous [z0, z1) level ranges, one per rank, sizes differing by at most one level."""
+def zslab_ranges(nz: int, world_size: int, weights: Optional[Sequence[float]] = None) -> List[Tuple[int, int]]:
+    """
+    Contiguous [z0, z1) level ranges, one per rank.
+
+    Without ``weights``: sizes differing by at most one level.  With ``weights`` (one number per level, normally the
+    pair counts from ``DeviceGeometry.level_pairs``: table bytes and gridding time of a slab are proportional to its
+    pairs, and the low levels of a radar grid hold several times the pairs of the high ones): the contiguous
+    partition that minimises the heaviest slab (exact, by dynamic programming; nz and world_size are tiny).
+    Ranks beyond the number of levels get empty slabs (z0 == z1).
+    """
     if world_size < 1 or nz < 0:
         raise ValueError("bad arguments")
-    base, extra = divmod(nz, world_size)
-    out, z = [], 0
-    for r in range(world_size):
-        n = base + (1 if r < extra else 0)
-        out.append((z, z + n))
-        z += n
+    if weights is None:
+        base, extra = divmod(nz, world_size)
+        out, z = [], 0
+        for r in range(world_size):
+            n = base + (1 if r < extra else 0)
+            out.append((z, z + n))
+            z += n
+        return out
+    w = [float(x) for x in weights]
+    if len(w) != nz or any(x < 0 for x in w):
+        raise ValueError("weights must hold one non-negative number per level")
+    pre = [0.0]
+    for x in w:
+        pre.append(pre[-1] + x)
+    k = min(world_size, max(nz, 1))
+    inf = float("inf")
+    # best[j][i]: minimal heaviest slab when the first i levels go to j slabs, every slab at least one level
+    best = [[inf] * (nz + 1) for _ in range(k + 1)]
+    cut = [[0] * (nz + 1) for _ in range(k + 1)]
+    best[0][0] = 0.0
+    for j in range(1, k + 1):
+        for i in range(j, nz + 1):
+            for m in range(j - 1, i):
+                cand = max(best[j - 1][m], pre[i] - pre[m])
+                if cand < best[j][i]:
+                    best[j][i], cut[j][i] = cand, m
+    bounds, i = [nz], nz
+    for j in range(k, 0, -1):
+        i = cut[j][i] if nz > 0 else 0
+        bounds.append(i)
+    bounds.reverse()
+    out = [(bounds[r], bounds[r + 1]) for r in range(k)] if nz > 0 else []
+    out += [(nz, nz)] * (world_size - len(out))
     return out
 
 
@@ -53,16 +88,20 @@ def _dist():
     return dist
 
 
-def allreduce_nanmax(plane, group=None, minimum: bool = False):
+def allreduce_nanmax(plane, group=None, minimum: bool = False, encoded: bool = False):
     """
     In-place combine of partial column-max (or -min) planes across ranks with NumPy's nanmax semantics:
     a pixel is NaN only if it is NaN on every rank.  `plane` is a torch tensor (CUDA with nccl, CPU with gloo).
+
+    ``encoded``: the plane comes from a ``ColumnMax(partial=True)`` request, i.e. the fused epilogue already wrote
+    -inf (+inf) where the slab has no data, and only the decode after the collective is left.  The sentinel doubles as
+    a value: a genuine -inf (+inf) column extremum comes back as NaN -- reflectivity-like fields never hold one.
     """
     import torch
     dist = _dist()
     sentinel = float("inf") if minimum else float("-inf")
-    nan = torch.isnan(plane)
-    plane.masked_fill_(nan, sentinel)
+    if not encoded:
+        plane.masked_fill_(torch.isnan(plane), sentinel)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(plane, op=dist.ReduceOp.MIN if minimum else dist.ReduceOp.MAX, group=group)
     plane.masked_fill_(plane == sentinel, float("nan"))
@@ -249,6 +288,112 @@ def ppi_zslab(request, grid_shape, grid_limits, z_range, slab_grids, group=None)
     out = ppi_zslab_partial(ppi_zslab_plan(request, grid_shape, grid_limits), z_range, slab_grids)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+    return out
+
+
+def _partial_requests(products):
+    import dataclasses
+    from .engine import CAPPI, PPI, ColumnMax, ColumnMean, ColumnMin, LevelPick
+    reqs = []
+    for p in products:
+        if isinstance(p, ColumnMean) or not isinstance(p, (ColumnMax, ColumnMin, CAPPI, PPI, LevelPick)):
+            raise ValueError(f"{type(p).__name__} has no z-slab form (use allreduce_nanmean on sums and counts)")
+        reqs.append(dataclasses.replace(p, partial=True))
+    return reqs
+
+
+def _reduce_kind(p) -> str:
+    from .engine import ColumnMax, ColumnMin
+    return "min" if isinstance(p, ColumnMin) else "max" if isinstance(p, ColumnMax) else "sum"
+
+
+def zslab_terms(slab_geom, fields, products, **grid_kwargs) -> List:
+    """This slab's TERMS of the requested 2-D products (torch tensors, one (F, ny, nx) plane set per request) from one
+    fused pass with ``partial=True`` requests and no 3-D grid: see `zslab_products`."""
+    import torch
+    from .engine import grid_fields
+    res = grid_fields(slab_geom, fields, products=_partial_requests(products), want_grid=False, **grid_kwargs)
+    return [pl if hasattr(pl, "is_cuda") else torch.from_numpy(pl) for pl in res["products"]]
+
+
+def zslab_merge(acc: List, terms: List, products) -> List:
+    """Merge another slab's terms into ``acc`` in place (what the all-reduce does between ranks), for a rank that walks
+    several slabs one after the other."""
+    import torch
+    for p, a, t in zip(products, acc, terms):
+        kind = _reduce_kind(p)
+        if kind == "max":
+            torch.maximum(a, t, out=a)
+        elif kind == "min":
+            torch.minimum(a, t, out=a)
+        else:
+            a.add_(t)
+    return acc
+
+
+def zslab_finish(terms: List, products, group=None) -> List:
+    """all-reduce(MAX | MIN | SUM) of the terms -- planes of one reduction kind and dtype travel in ONE buffer -- then
+    decode: the -inf / +inf "no data" sentinel of COLMAX / COLMIN becomes NaN, a float64 CAPPI blend is rounded to
+    float32 (reference products.py:412).  In place where the dtype allows; the finished planes are returned."""
+    import torch
+    from .engine import CAPPI, ColumnMax, ColumnMin
+    dist = _dist()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        ops = {"max": dist.ReduceOp.MAX, "min": dist.ReduceOp.MIN, "sum": dist.ReduceOp.SUM}
+        buckets: Dict[Tuple[str, object], List[int]] = {}
+        for i, (p, pl) in enumerate(zip(products, terms)):
+            buckets.setdefault((_reduce_kind(p), pl.dtype), []).append(i)
+        for (kind, _), idxs in buckets.items():
+            if len(idxs) == 1:
+                dist.all_reduce(terms[idxs[0]], op=ops[kind], group=group)
+                continue
+            flat = torch.cat([terms[i].reshape(-1) for i in idxs])
+            dist.all_reduce(flat, op=ops[kind], group=group)
+            off = 0
+            for i in idxs:
+                n = terms[i].numel()
+                terms[i].copy_(flat[off:off + n].view_as(terms[i]))
+                off += n
+    out = []
+    for p, pl in zip(products, terms):
+        if isinstance(p, ColumnMin):
+            pl.masked_fill_(pl == float("inf"), float("nan"))
+        elif isinstance(p, ColumnMax):
+            pl.masked_fill_(pl == float("-inf"), float("nan"))
+        elif isinstance(p, CAPPI) and pl.dtype == torch.float64:
+            pl = pl.to(torch.float32)
+        out.append(pl)
+    return out
+
+
+def zslab_products(slab_geom, fields, products, group=None, timings: Optional[dict] = None, **grid_kwargs) -> List:
+    """
+    2-D products of a grid that is split into z-slabs across ranks, from ONE fused pass per rank and ONE collective
+    per reduction kind; the finished planes are returned on every rank, bit-identical to the unsharded products.
+
+    Every request (``ColumnMax``, ``ColumnMin``, ``CAPPI``, ``PPI``, ``LevelPick``) is issued with ``partial=True``: the
+    epilogue of ``grid_fields(slab_geom, ..., want_grid=False)`` writes this slab's TERM of the product -- running max
+    with -inf for "no data here"; for the level blends ``w_lo*g[lo] + w_hi*g[hi]`` (reference products.py:294-304, 411)
+    the products of the levels the slab owns and -0.0, the neutral element of IEEE addition, for the others -- so no
+    slab 3-D grid is materialised and no torch arithmetic surrounds the collective: all-reduce(MAX | MIN | SUM), decode
+    the sentinel, round a float64 CAPPI blend to float32.  ``fields`` are torch CUDA tensors (NCCL) or NumPy arrays (the
+    planes then go through torch CPU tensors: gloo, the CPU tests).  ``timings`` (optional dict) receives the wall times
+    ``apply_ms`` and ``allreduce_ms``.
+    """
+    import time
+    import torch
+    t0 = time.perf_counter()
+    terms = zslab_terms(slab_geom, fields, products, **grid_kwargs)
+    cuda = bool(terms) and terms[0].is_cuda
+    if cuda:
+        torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    out = zslab_finish(terms, products, group=group)
+    if cuda:
+        torch.cuda.synchronize()
+    if timings is not None:
+        timings["apply_ms"] = (t1 - t0) * 1e3
+        timings["allreduce_ms"] = (time.perf_counter() - t1) * 1e3
     return out
 
 

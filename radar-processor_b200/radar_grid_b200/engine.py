@@ -77,6 +77,29 @@ class DeviceGeometry:
         del keep
         return cls(h, ctx, grid_shape, grid_limits, z_range)
 
+    @staticmethod
+    def level_pairs(gate_x, gate_y, gate_z, grid_shape, grid_limits, radar_altitude=0.0, min_radius=250.0,
+                    beam_factor=0.01746, toa=17000.0, column_stride: int = 4, z_range=None,
+                    ctx: Optional[N.Context] = None) -> np.ndarray:
+        """Pair count of every z-level (int64, scaled from every ``column_stride``-th column; exact for stride 1) without
+        building a table: the weights ``distributed.zslab_ranges`` balances z-slabs with."""
+        ctx = ctx or N.default_context()
+        spec = _grid_spec(grid_shape, grid_limits, z_range)
+        out = np.zeros(spec.z_end - spec.z_begin, dtype=np.int64)
+        if N.is_device_array(gate_x):
+            keep, space = (gate_x, gate_y, gate_z), N.RG_DEVICE
+            ptrs = [N.device_ptr(a) for a in keep]
+            n = int(gate_x.numel())
+        else:
+            keep = tuple(np.ascontiguousarray(np.asarray(a).ravel(), dtype=np.float32) for a in (gate_x, gate_y, gate_z))
+            ptrs, space, n = [N.host_ptr(a) for a in keep], N.RG_HOST, keep[0].shape[0]
+        with N.torch_stream_order(ctx, space == N.RG_DEVICE):
+            N.check(N.lib().rg_geometry_level_pairs(ctx.handle, ptrs[0], ptrs[1], ptrs[2], n, space, C.byref(spec),
+                                                    float(radar_altitude), float(min_radius), float(beam_factor), float(toa),
+                                                    int(column_stride), out.ctypes.data_as(C.POINTER(C.c_int64))))
+        del keep
+        return out
+
     @classmethod
     def from_csr(cls, indptr, gate_indices, weights, grid_shape, grid_limits, n_gates: int, z_range=None,
                  ctx: Optional[N.Context] = None) -> "DeviceGeometry":
@@ -180,6 +203,7 @@ class ColumnMax:
     z_max_idx: Optional[int] = None
     z_min_alt: Optional[float] = None
     z_max_alt: Optional[float] = None
+    partial: bool = False      # z-slab term: "no data in this slab" is -inf (+inf for ColumnMin), see distributed.zslab_products
     kind = N.RG_PROD_COLMAX
     name = "column_max"
 
@@ -188,7 +212,7 @@ class ColumnMax:
                                   self.z_max_alt, have_geometry)
         if hi < lo:
             raise ValueError("zero-size array to reduction operation has no identity (empty z range)")
-        return N.Product(kind=self.kind, z_lo=lo, z_hi=hi), np.float32
+        return N.Product(kind=self.kind, z_lo=lo, z_hi=hi, partial=int(self.partial)), np.float32
 
 
 class ColumnMin(ColumnMax):
@@ -200,15 +224,33 @@ class ColumnMean(ColumnMax):
     kind = N.RG_PROD_COLMEAN
     name = "column_mean"
 
+    def resolve(self, grid_shape, grid_limits, have_geometry=True):
+        lo, hi = resolve_z_limits(grid_shape[0], grid_limits, self.z_min_idx, self.z_max_idx, self.z_min_alt,
+                                  self.z_max_alt, have_geometry)
+        if hi < lo:
+            # np.nanmean of an empty slice (products.py:578-580) is an all-NaN plane plus a RuntimeWarning, not an error
+            warnings.warn("Mean of empty slice", RuntimeWarning, stacklevel=3)
+            return None, np.float32
+        return N.Product(kind=self.kind, z_lo=lo, z_hi=hi), np.float32
+
 
 @dataclass
 class CAPPI:
     """constant_altitude_ppi — reference products.py:317-415."""
     altitude: float
     interpolation: str = "linear"
+    partial: bool = False      # z-slab term of the blend (sum over the owned levels of weight * level), see distributed.zslab_products
     name = "cappi"
 
     def resolve(self, grid_shape, grid_limits, have_geometry=True):
+        pr, dt = self._resolve(grid_shape, grid_limits)
+        if pr is not None and self.partial:
+            pr.partial = 1
+            if pr.mode == N.RG_BLEND_F64:
+                dt = np.float64          # the float64 blend is rounded to float32 only after the ranks' terms are added
+        return pr, dt
+
+    def _resolve(self, grid_shape, grid_limits):
         nz = grid_shape[0]
         z_min, z_max = grid_limits[0]
         altitude = self.altitude
@@ -246,12 +288,13 @@ class LevelPick:
     """One level of the grid by its GLOBAL index (0 .. nz-1).  Not a reference product by itself: it is the term a
     z-slab contributes to a CAPPI whose two levels live in different slabs (distributed.cappi_zslab)."""
     level: int
+    partial: bool = False      # z-slab term: the level where the slab owns it, -0.0 elsewhere
     name = "level"
 
     def resolve(self, grid_shape, grid_limits, have_geometry=True):
         if not (0 <= int(self.level) < grid_shape[0]):
             raise ValueError(f"level {self.level} outside the grid (nz = {grid_shape[0]})")
-        return N.Product(kind=N.RG_PROD_LEVEL, mode=N.RG_BLEND_PICK, z_lo=int(self.level)), np.float32
+        return N.Product(kind=N.RG_PROD_LEVEL, mode=N.RG_BLEND_PICK, z_lo=int(self.level), partial=int(self.partial)), np.float32
 
 
 @dataclass
@@ -261,6 +304,7 @@ class PPI:
     interpolation: str = "linear"
     earth_curvature: bool = True
     ke: float = EFFECTIVE_RADIUS_FACTOR
+    partial: bool = False      # z-slab term of the per-pixel blend, see distributed.zslab_products
     name = "ppi"
 
     def resolve(self, grid_shape, grid_limits, have_geometry=True):
@@ -269,7 +313,7 @@ class PPI:
         elevation_rad = np.radians(self.elevation_angle)              # products.py:70
         ke_re = self.ke * EARTH_RADIUS
         pr = N.Product(kind=N.RG_PROD_BEAM, mode=0 if self.interpolation == "linear" else 1,
-                       earth_curvature=1 if self.earth_curvature else 0,
+                       earth_curvature=1 if self.earth_curvature else 0, partial=int(self.partial),
                        sin_elev=float(np.sin(elevation_rad)),
                        cos_elev_clamped=float(np.maximum(np.cos(elevation_rad), 0.01)),
                        tan_elev=float(np.tan(elevation_rad)), ke_re=float(ke_re), ke_re_sq=float(ke_re ** 2))

@@ -34,6 +34,31 @@ def test_zslab_ranges_cover_contiguously():
         assert max(sizes) - min(sizes) <= 1
 
 
+def test_zslab_ranges_balanced_by_weights():
+    """With per-level weights the partition minimises the heaviest slab (checked against brute force on small cases),
+    stays contiguous, and hands empty slabs to ranks beyond the number of levels."""
+    import itertools
+    rng = np.random.default_rng(3)
+    for nz, w in ((7, 3), (9, 4), (6, 6), (5, 2)):
+        weights = rng.integers(0, 50, size=nz).astype(float)
+        r = D.zslab_ranges(nz, w, weights=weights)
+        assert r[0][0] == 0 and r[-1][1] == nz and len(r) == w and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        got = max(weights[a:b].sum() for a, b in r)
+        best = min(max(weights[a:b].sum() for a, b in zip((0,) + c, c + (nz,)))
+                   for c in itertools.combinations(range(1, nz), w - 1)) if w > 1 else weights.sum()
+        assert got == best, (nz, w, got, best)
+    r = D.zslab_ranges(3, 5, weights=[4.0, 1.0, 1.0])
+    assert r == [(0, 1), (1, 2), (2, 3), (3, 3), (3, 3)]
+    # a radar-like profile: the low levels hold most of the pairs
+    prof = [100, 90, 70, 50, 30, 20, 10, 5, 2, 1]
+    r = D.zslab_ranges(10, 4, weights=prof)
+    loads = [sum(prof[a:b]) for a, b in r]
+    even = [sum(prof[a:b]) for a, b in D.zslab_ranges(10, 4)]
+    assert max(loads) == 118 < max(even) == 260
+    with pytest.raises(ValueError):
+        D.zslab_ranges(4, 2, weights=[1.0, 2.0])
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -91,6 +116,22 @@ def _worker(rank, world, port, out_dir):
             assert got.dtype == np.float32 and np.array_equal(got, np.asarray(want, dtype=np.float32), equal_nan=True), \
                 f"z-slab CAPPI {req} != unsharded CAPPI"
             assert np.array_equal(np.signbit(got), np.signbit(np.asarray(want, dtype=np.float32)))
+        # --- zslab_finish: the terms a fused partial=True pass would write (emulated from the reference grid), batched
+        # all-reduce(MAX) + all-reduce(SUM) over gloo, decode; equals the reference products
+        from radar_grid_b200 import ColumnMax as CMax, LevelPick
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            cm = np.nanmax(grid[z0:z1], axis=0) if z1 > z0 else np.full((ny, nx), np.nan, np.float32)
+        t_max = torch.from_numpy(np.where(np.isnan(cm), -np.inf, cm).astype(np.float32)[None].copy())
+        lvl = boundary                                                   # owned by rank 1 only
+        t_pick = torch.from_numpy((grid[lvl] if z0 <= lvl < z1 else np.full((ny, nx), -0.0, np.float32))[None].copy())
+        lvl2 = 0
+        t_pick2 = torch.from_numpy((grid[lvl2] if z0 <= lvl2 < z1 else np.full((ny, nx), -0.0, np.float32))[None].copy())
+        reqs = [CMax(), LevelPick(lvl), LevelPick(lvl2)]
+        fin = D.zslab_finish([t_max, t_pick, t_pick2], reqs)
+        assert np.array_equal(fin[0].numpy()[0], g["colmax"], equal_nan=True)
+        assert np.array_equal(fin[1].numpy()[0], grid[lvl], equal_nan=True) and np.array_equal(fin[2].numpy()[0], grid[lvl2], equal_nan=True)
         # --- z-slab PPI: per-pixel level pairs, gathered from the slab's grid, one all-reduce(sum)
         from radar_grid_b200 import PPI
         slab_t = torch.from_numpy(grid[z0:z1][None].copy())

@@ -508,3 +508,55 @@ def test_empty_zslab_still_writes_its_product_planes():
                          products=[rg.ColumnMax(), rg.LevelPick(2), rg.ColumnMean()], out_products=outs)
     for p in res["products"]:
         assert np.isnan(p).all()
+
+
+def test_zslab_fused_terms_of_every_product_kind_merge_to_the_unsharded_products():
+    """distributed.zslab_terms / zslab_merge / zslab_finish: ONE fused pass per slab with partial=True requests (no slab
+    3-D grid, no torch arithmetic before the collective) -- COLMAX / COLMIN with -inf / +inf for "no data", CAPPI
+    (float32 and float64 blends, level pick), PPI (linear -> float64, nearest) and LevelPick as sums over the owned
+    levels with -0.0 elsewhere -- merged the way all-reduce(MAX | MIN | SUM) merges ranks, is bit-identical to the
+    unsharded fused products, for balanced (uneven) slabs and with an empty slab in the list."""
+    import torch
+    from radar_grid_b200 import distributed as D
+    spec, radar, gates, fields, g = golden_case("small")
+    names = list(fields)
+    data = [np.ma.getdata(fields[n]) for n in names]
+    masks = [np.ma.getmaskarray(fields[n]) for n in names]
+    nz = spec.grid_shape[0]
+    step = spec.grid_limits[0][1] / (nz - 1)
+    lims64 = tuple(tuple(np.float64(v) for v in ax) for ax in spec.grid_limits)
+    pairs = rg.DeviceGeometry.level_pairs(*gates, spec.grid_shape, spec.grid_limits, min_radius=spec.min_radius,
+                                          beam_factor=spec.beam_factor, toa=spec.toa, column_stride=1)
+    whole = build(spec, gates, "barnes2", 0)
+    indptr = whole.export_csr()[0].astype(np.int64)
+    ny, nx = spec.grid_shape[1:]
+    np.testing.assert_array_equal(pairs, np.diff(indptr[::ny * nx]))         # exact census at stride 1
+    approx = rg.DeviceGeometry.level_pairs(*gates, spec.grid_shape, spec.grid_limits, min_radius=spec.min_radius,
+                                           beam_factor=spec.beam_factor, toa=spec.toa, column_stride=3)
+    assert abs(approx.sum() - pairs.sum()) < 0.1 * pairs.sum()
+    ranges = D.zslab_ranges(nz, 4, weights=pairs)
+    assert ranges[0][0] == 0 and ranges[-1][1] == nz and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+    ranges = ranges[:2] + [(ranges[1][1], ranges[1][1])] + ranges[2:]         # plus an empty slab
+    whole.ctx.set_option("group_width", 8)            # same summation order for slabs and whole grid
+    try:
+        for lims in (spec.grid_limits, lims64):
+            reqs = [rg.ColumnMax(), rg.ColumnMin(z_min_idx=1), rg.CAPPI((ranges[0][1] - 0.6) * step), rg.CAPPI(2.0 * step),
+                    rg.CAPPI(1234.5, "nearest"), rg.PPI(2.3)]
+            reqs2 = [rg.ColumnMax(z_max_idx=nz - 2), rg.PPI(6.9, "nearest"), rg.PPI(0.5, earth_curvature=False), rg.LevelPick(nz - 1),
+                     rg.CAPPI(spec.grid_limits[0][1] + 10.0)]
+            for rq in (reqs, reqs2):
+                whole.grid_limits = lims
+                want = rg.grid_fields(whole, data, masks=masks, want_grid=False, products=rq)["products"]
+                acc = None
+                for zr in ranges:
+                    slab = build(spec, gates, "barnes2", 0, z_range=zr)
+                    slab.grid_limits = lims
+                    terms = D.zslab_terms(slab, data, masks=masks, products=rq)
+                    acc = terms if acc is None else D.zslab_merge(acc, terms, rq)
+                got = D.zslab_finish(acc, rq)
+                for p, a, b in zip(rq, got, want):
+                    assert_same(a.numpy(), b, f"z-slab {type(p).__name__} {p}")
+                    assert np.array_equal(np.signbit(a.numpy()), np.signbit(b))
+    finally:
+        whole.grid_limits = spec.grid_limits
+        whole.ctx.set_option("group_width", 0)

@@ -6,6 +6,8 @@ mkdir -p gpurun_out
 L=radar-processor_b200/lib
 PYT="tests -m gpu"
 if [ "${1:-}" = "-t" ]; then PYT="$2"; shift 2; fi
+# -q: everything but the three-minute cfg5 brute-force test
+if [ "${1:-}" = "-q" ]; then PYT="tests -m gpu --deselect tests/test_gpu_configs.py::test_cfg5_slab_rows_against_bruteforce_and_colmax_against_the_oracle"; shift; fi
 if [ -n "$PYT" ]; then echo "== pytest $PYT"; timeout 1500 python -m pytest $PYT -q -p no:cacheprovider -x 2>&1 | tail -15; fi
 run() { # name lib extra
   out=gpurun_out/ab_$1.json
