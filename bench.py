@@ -16,8 +16,9 @@ N>1: weak scaling, no data-path collective — every rank holds a replica of the
 volumes (the reference's time-series batch shard, BASELINE.json configs[3]); value = all ranks' voxels /
 max-over-ranks device time.
 
---impl reference times the CPU path (the NumPy oracle port of the pure-Python reference, see oracle/) on a
-bounded sample of the same workload on the box's host cores.
+--impl reference times the reference's own CPU path — the genuine modules byte-compiled into oracle/_ref where they
+travelled with the snapshot, else the NumPy oracle port — on the SAME workload (all levels, all fields) on the box's
+host cores, one worker process per field.
 """
 
 import argparse
@@ -48,12 +49,26 @@ def load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def kernel_source_hash():
+    """SHA-256 over the CUDA sources: profiles/apply_traffic.json is stamped with it when it is regenerated from an ncu
+    capture (tools/ncu_summary.py --traffic), so a stale DRAM-traffic figure is never reported for a changed kernel."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("rg_apply.cu", "rg_geometry.cu", "rg_api.cu", "rg_internal.cuh"):
+        with open(os.path.join(ROOT, "radar-processor_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def measured_traffic(workload):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the apply kernel from the committed ncu capture (per launch)."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of the apply kernel from the committed ncu capture (per launch);
+    None when the capture belongs to another workload or to other kernel sources."""
     try:
         with open(os.path.join(ROOT, "profiles", "apply_traffic.json")) as fh:
             t = json.load(fh)
-        return float(t["traffic_bytes_per_launch"]) if t.get("workload") == workload else None
+        if t.get("workload") != workload or t.get("source_sha256") != kernel_source_hash():
+            return None
+        return float(t["traffic_bytes_per_launch"])
     except Exception:
         return None
 
@@ -252,6 +267,23 @@ def run_b200(args):
             t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t.item())
+        # the same pipeline for a products-only request (COLMAX + CAPPI planes, no 3-D grid leaves the GPU): what an
+        # operational product server asks for; 194 MB of the D2H traffic above become 9 MB
+        pslots = [{"fields": sl["fields"], "mask_invalid": True, "products": products, "want_grid": False,
+                   "out_products": sl["out_products"]} for sl in slots]
+        pipe.map([pslots[i % n_slots] for i in range(2 * n_slots)])
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        pipe.map([pslots[i % n_slots] for i in range(e2e_steps)])
+        torch.cuda.synchronize()
+        e2e_prod_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2e_prod_s], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_prod_s = float(t.item())
+        pipe.close()
         pin_grids = slots[0]["out_grids"]
         h2d = F * G * 4
         d2h = F * V * 4 + len(products) * F * ncol * 4
@@ -294,14 +326,80 @@ def run_b200(args):
                 "note": "pinned host fields in, 3-D grids + COLMAX + CAPPI planes back to pinned host memory, every volume "
                         "copied in full; VolumePipeline -> grid_fields() -> rg_apply(RG_HOST) on several streams (see \"streams\") so that copies of "
                         "neighbouring volumes overlap the kernels"},
+        "e2e_products_only": {"value": world * F * V * e2e_steps / e2e_prod_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                              "d2h_bytes_per_step": len(products) * F * ncol * 4, "steps": e2e_steps,
+                              "ms_per_step": e2e_prod_s / e2e_steps * 1e3, "streams": n_slots,
+                              "note": "same pipeline and inputs, want_grid=False: COLMAX + CAPPI planes only come back"},
         "gpu_launches": launches,
     }
+    if world > 1:
+        line["zslab"] = zslab_record(rg, N, S, spec, gates, raw, dev, ctx, world, rank, local_rank)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_from_table(dev, spec, fields_ma)
     if world > 1:
         dist.destroy_process_group()
     return line if rank == 0 else None
+
+
+def zslab_record(rg, N, S, spec, gates, raw, dev, ctx, world, rank, local_rank):
+    """
+    The z-slab shard of the SAME volume on the same ranks (N > 1 only): the grid is cut into `world` slabs balanced by
+    pair count (level census, DeviceGeometry.level_pairs), every rank builds and grids only its slab (COLMAX + CAPPI
+    4000 m as fused z-slab terms, no 3-D grid) and ONE all-reduce(MAX) + ONE all-reduce(SUM) over NCCL finish the
+    planes.  Reported: wall ms per volume including the collectives (max over ranks), the collectives alone, the
+    unsharded products-only pass on one GPU, and whether the planes are bit-identical to the unsharded ones.
+    """
+    import torch
+    import torch.distributed as dist
+    from radar_grid_b200 import distributed as D
+    F = len(spec.fields)
+    nz = spec.grid_shape[0]
+    kw = dict(min_radius=spec.min_radius, beam_factor=spec.beam_factor, toa=spec.toa)
+    census = rg.DeviceGeometry.level_pairs(*gates, spec.grid_shape, spec.grid_limits, column_stride=4, ctx=ctx, **kw)
+    ranges = D.zslab_ranges(nz, world, weights=census)
+    t0 = time.perf_counter()
+    slab = rg.DeviceGeometry.build(*gates, spec.grid_shape, spec.grid_limits, weighting=spec.weighting, z_range=ranges[rank], ctx=ctx, **kw)
+    build_s = time.perf_counter() - t0
+    products = [rg.ColumnMax(), rg.CAPPI(CAPPI_ALT)]
+    stream = torch.cuda.current_stream()
+    dfields = [torch.from_numpy(r).cuda() for r in raw]
+    ctx.set_option("group_width", 4)                       # same summation order for the slabs and the unsharded table
+    try:
+        want = rg.grid_fields(dev, dfields, mask_invalid=True, products=products, want_grid=False, ctx=ctx)["products"]
+        got = D.zslab_products(slab, dfields, products, mask_invalid=True, ctx=ctx)
+        identical = all(torch.equal(a.nan_to_num(-1e30), b.nan_to_num(-1e30)) for a, b in zip(got, want))
+        reps, wall, coll, apply_ms = 20, [], [], []
+        for _ in range(3 + reps):
+            dist.barrier()
+            torch.cuda.synchronize()
+            tm = {}
+            t0 = time.perf_counter()
+            D.zslab_products(slab, dfields, products, mask_invalid=True, ctx=ctx, timings=tm)
+            torch.cuda.synchronize()
+            wall.append((time.perf_counter() - t0) * 1e3)
+            coll.append(tm["allreduce_ms"])
+            apply_ms.append(tm["apply_ms"])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            rg.grid_fields(dev, dfields, mask_invalid=True, products=products, want_grid=False, ctx=ctx)
+        torch.cuda.synchronize()
+        unsharded_ms = (time.perf_counter() - t0) * 1e3 / reps
+    finally:
+        ctx.set_option("group_width", int(os.environ.get("RG_GROUP_WIDTH") or 0))
+    stats = torch.tensor([float(np.median(wall[3:])), float(np.median(coll[3:])), float(np.median(apply_ms[3:])), build_s,
+                          float(slab.n_pairs), float(identical)], dtype=torch.float64, device="cuda")
+    allr = [torch.zeros_like(stats) for _ in range(world)]
+    dist.all_gather(allr, stats)
+    allr = torch.stack(allr).cpu().numpy()
+    slab.close()
+    return {"what": f"{spec.name} in {world} z-slabs balanced by pair count, COLMAX + CAPPI {CAPPI_ALT:.0f} m as fused z-slab terms, "
+                    "all-reduce(MAX) + all-reduce(SUM) over NCCL; wall clock per volume incl. the collectives, median of 20",
+            "slab_levels": [list(r) for r in ranges], "slab_pairs": [int(v) for v in allr[:, 4]],
+            "wall_ms": float(allr[:, 0].max()), "allreduce_ms": float(allr[:, 1].max()), "slab_apply_ms_per_rank": [float(v) for v in allr[:, 2]],
+            "slab_build_s_per_rank": [float(v) for v in allr[:, 3]], "unsharded_ms_one_gpu": unsharded_ms,
+            "speedup_vs_one_gpu": unsharded_ms / float(allr[:, 0].max()), "identical": bool(allr[:, 5].min() == 1.0)}
 
 
 def cpu_baseline_from_table(dev, spec, fields_ma):
@@ -322,7 +420,9 @@ def cpu_baseline_from_table(dev, spec, fields_ma):
 
 
 # ---------------------------------------------------------------------------------------------------------
-# reference arm: the CPU path (oracle port of the pure-Python reference) on the host cores
+# reference arm: the reference's own CPU implementation of the path on the host cores — the genuine modules from
+# oracle/_ref (byte-compiled from /root/reference by oracle/build_ref.py) when they travelled with the snapshot, else
+# the NumPy oracle port.  Same workload as our arm: all levels, all fields, COLMAX + the real CAPPI blend.
 # ---------------------------------------------------------------------------------------------------------
 _REF = {}
 
@@ -334,73 +434,114 @@ def _ref_build_level(iz):
                                 beam_factor=s.beam_factor, weighting=s.weighting, toa=s.toa, z_range=(iz, iz + 1))
 
 
-def _ref_apply(task):
-    from oracle import radar_grid_oracle as O
-    iz, name = task
+def _ref_field(name):
+    """One field through the CPU path: apply_geometry + column_max + constant_altitude_ppi (single-threaded NumPy, as the
+    reference runs it); the fields of a volume are independent, so they run in parallel worker processes."""
+    import warnings
     s = _REF["spec"]
-    indptr, idx, w = _REF["tables"][iz]
-    return iz, name, O.apply_geometry(indptr, idx, w, (1, s.grid_shape[1], s.grid_shape[2]), _REF["fields"][name])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if _REF["ref"] is not None:
+            ref, geom = _REF["ref"], _REF["geom"]
+            grid = ref.interpolate.apply_geometry(geom, _REF["fields"][name])
+            cmax = ref.products.column_max(grid)
+            cap = ref.products.constant_altitude_ppi(grid, geom, CAPPI_ALT)
+        else:
+            from oracle import radar_grid_oracle as O
+            indptr, idx, w = _REF["table"]
+            grid = O.apply_geometry(indptr, idx, w, s.grid_shape, _REF["fields"][name])
+            cmax = O.column_reduce("max", grid)
+            cap = O.cappi(grid, s.grid_shape, s.grid_limits, CAPPI_ALT)
+    return name, float(np.nansum(cmax)), float(np.nansum(cap))
+
+
+def _ref_table(spec, gates, cores, genuine):
+    """The neighbour table of the whole grid, built by the reference itself (or the port), cached in /tmp for the other
+    invocations of the same round-end run (the reference's own save_geometry / load_geometry idea)."""
+    import multiprocessing as mp
+    import tempfile
+    tag = "reference" if genuine else "port"
+    path = os.path.join(tempfile.gettempdir(), f"rg_bench_{tag}_table_{spec.name}.npz")
+    t0 = time.perf_counter()
+    if os.path.exists(path):
+        with np.load(path) as z:
+            return (z["indptr"], z["gate_indices"], z["weights"]), time.perf_counter() - t0, "loaded from " + path
+    if genuine:
+        from oracle import build_ref
+        ref = build_ref.load()
+        with tempfile.TemporaryDirectory() as tmp:
+            g = ref.compute.compute_grid_geometry(*gates, spec.grid_shape, spec.grid_limits, tmp, min_radius=spec.min_radius,
+                                                  beam_factor=spec.beam_factor, weighting=spec.weighting, toa=spec.toa,
+                                                  n_workers=max(1, cores - 1))
+        table = (g.indptr, g.gate_indices, g.weights)
+    else:
+        with mp.get_context("fork").Pool(cores) as pool:
+            parts = dict(pool.map(_ref_build_level, range(spec.grid_shape[0])))
+        ptr, idx, w, base = [np.zeros(1, dtype=np.int64)], [], [], 0
+        for iz in range(spec.grid_shape[0]):
+            p, i, ww = parts[iz]
+            ptr.append(np.asarray(p[1:], dtype=np.int64) + base)
+            base += int(p[-1])
+            idx.append(i)
+            w.append(ww)
+        table = (np.concatenate(ptr), np.concatenate(idx), np.concatenate(w))
+    try:
+        np.savez(path, indptr=table[0], gate_indices=table[1], weights=table[2])
+    except OSError:
+        pass
+    return table, time.perf_counter() - t0, "built"
 
 
 def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return None
     import multiprocessing as mp
+    import logging
     from radar_grid_b200 import synthetic as S
-    from oracle import radar_grid_oracle as O
+    from oracle import build_ref
+    logging.disable(logging.INFO)
     spec = S.SPECS[args.workload]
     nz, ny, nx = spec.grid_shape
     F = len(spec.fields)
     cores = os.cpu_count() or 1
-    # bounded sample: keep the whole --steps/--warmup run within a few minutes whatever K and W are
-    budget_s = 150.0 / max(1, args.steps + args.warmup)
-    n_levels = int(max(1, min(5, budget_s / 0.4, nz)))
-    step_z = max(1, nz // n_levels)
-    levels = list(range(0, nz, step_z))[:n_levels]
-    cappi_level = int(round((CAPPI_ALT - spec.grid_limits[0][0]) / ((spec.grid_limits[0][1] - spec.grid_limits[0][0]) / (nz - 1))))
-    if cappi_level not in levels and 0 <= cappi_level < nz:
-        levels[1 if len(levels) > 1 else 0] = cappi_level
-        levels = sorted(set(levels))
+    genuine = build_ref.available()
     gates = S.gate_coordinates(spec)
-    _REF.update(spec=spec, gates=gates)
-    ctxmp = mp.get_context("fork")
-    t0 = time.perf_counter()
-    with ctxmp.Pool(min(cores, len(levels))) as pool:
-        _REF["tables"] = dict(pool.map(_ref_build_level, levels))
-    build_s = time.perf_counter() - t0
-    _REF["fields"] = S.make_fields(spec, seed=0, gates=gates)
-    tasks = [(iz, name) for iz in levels for name in spec.fields]
-    workers = min(cores, len(tasks))
-    pairs = sum(int(t[0][-1]) for t in _REF["tables"].values())
-
-    def step(pool):
-        grids = {}
-        for iz, name, g in pool.map(_ref_apply, tasks):
-            grids[(iz, name)] = g[0]
-        for name in spec.fields:
-            stack = np.stack([grids[(iz, name)] for iz in levels])
-            O.column_reduce("max", stack)
-            _ = stack[levels.index(cappi_level)] if cappi_level in levels else None
-
-    with ctxmp.Pool(workers) as pool:
+    _REF.update(spec=spec, gates=gates, ref=None)
+    table, table_s, how = _ref_table(spec, gates, cores, genuine)
+    if genuine:
+        ref = build_ref.load()
+        _REF["ref"] = ref
+        _REF["geom"] = ref.geometry.GridGeometry(grid_shape=spec.grid_shape, grid_limits=spec.grid_limits, indptr=table[0],
+                                                 gate_indices=table[1], weights=table[2], toa=spec.toa)
+        radar = S.SyntheticRadar(spec, seed=0)
+        _REF["fields"] = {name: ref.utils.get_field_data(radar, name) for name in spec.fields}
+    else:
+        _REF["table"] = table
+        _REF["fields"] = S.make_fields(spec, seed=0, gates=gates)
+    workers = min(cores, F)
+    with mp.get_context("fork").Pool(workers) as pool:
         for _ in range(args.warmup):
-            step(pool)
+            pool.map(_ref_field, spec.fields)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            step(pool)
+            sums = pool.map(_ref_field, spec.fields)
         dt = time.perf_counter() - t0
-    value = F * len(levels) * ny * nx * args.steps / dt
-    sample = (f"z-levels {levels} of {nz} (table built by the oracle in {build_s:.0f} s, untimed), all {F} fields: "
-              f"apply_geometry per (level, field) + COLMAX over the sampled levels + CAPPI level pick; "
-              f"{workers} worker processes")
+    value = F * nz * ny * nx * args.steps / dt
+    kind = "reference" if genuine else "port"
+    sample = (f"the full workload, nothing sampled: all {nz} levels x {F} fields per step through "
+              f"{'the reference modules (oracle/_ref)' if genuine else 'the NumPy oracle port'}: apply_geometry + column_max + "
+              f"constant_altitude_ppi({CAPPI_ALT:.0f} m) per field, {workers} worker processes (one field each, single-threaded "
+              f"NumPy as in the reference); table of {int(table[0][-1])} pairs {how} in {table_s:.0f} s by "
+              f"{'compute_grid_geometry, ' + str(max(1, cores - 1)) + ' workers' if genuine else 'the port'} (untimed, as on our arm)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded storm-cell volume, SURVEY.md 8d)",
-        "config": {"workload": f"{spec.name}: CPU path of the reference (NumPy oracle port; the reference is pure Python, "
-                               f"nothing to compile into oracle/_ref), bounded sample", "pairs_in_sample": pairs},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample,
-                         "host_cpus": cores},
+        "config": {"workload": f"{spec.name}: {len(spec.elevations)} sweeps x {spec.nrays} x {spec.ngates} gates, fields "
+                               f"{'+'.join(spec.fields)} -> {nz}x{ny}x{nx} grid ({spec.weighting}); per step: {F}-field 3-D grids + "
+                               f"COLMAX + CAPPI {CAPPI_ALT:.0f} m on the CPU path of the reference",
+                   "pairs": int(table[0][-1]), "voxels": nz * ny * nx, "fields": F, "colmax_checksums": [s[1] for s in sums]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": kind, "sample": sample, "host_cpus": cores},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

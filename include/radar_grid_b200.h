@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RG_ABI_VERSION 1
+#define RG_ABI_VERSION 2
 #define RG_MAX_FIELDS 8      /* fields gridded per neighbour-table pass (one index load serves all) */
 #define RG_MAX_RULES 8       /* fused QC range rules per apply call */
 #define RG_MAX_SLICES 4      /* CAPPI / PPI planes per apply call */
@@ -155,8 +155,30 @@ typedef enum rg_blend_mode {
     RG_BLEND_F64_OUT64 = 3     /* same in float64, float64 output (PPI 'linear')     (float64 out) */
 } rg_blend_mode;
 
-/* One 2-D product.  `out` receives n_fields planes of ny*nx elements, field-major.  z indices are
- * GLOBAL level indices (0..nz-1), inclusive. */
+/* Image form of a 2-D product, written by the same epilogue that finishes the product so that only ny*nx*4 bytes per
+ * field have to leave the GPU: GridFilter thresholds (reference filters.py:631-746, applied in order, each replacing
+ * the selected pixels by its fill value), then the colormap of reference geotiff.py:70-145 -- no-data test (== fill_value,
+ * or NaN when has_fill_value is 0), Normalize(vmin, vmax, clip=True) in the plane's arithmetic type, LUT index
+ * int(x * lut_entries) with 1.0 mapped to the last entry and NaN to the "bad" entry lut_entries + 2, alpha 0 for
+ * no-data.  `lut` holds lut_entries + 3 RGBA byte quadruples, already scaled ((lut * 255).astype(uint8): matplotlib's
+ * Colormap._lut including its under / over / bad rows), in the memory space of the call. */
+#define RG_MAX_IMAGE_FILTERS 4
+typedef struct rg_image {
+    int32_t n_filters;                               /* 0..RG_MAX_IMAGE_FILTERS */
+    int32_t filter_kind[RG_MAX_IMAGE_FILTERS];       /* rg_plane_filter_kind */
+    double filter_a[RG_MAX_IMAGE_FILTERS];
+    double filter_b[RG_MAX_IMAGE_FILTERS];
+    double filter_fill[RG_MAX_IMAGE_FILTERS];
+    double vmin, vmax;                               /* vmin <= vmax, finite */
+    double fill_value;
+    int32_t has_fill_value;
+    int32_t lut_entries;                             /* N (256 for matplotlib colormaps), 1..4096 */
+    const uint8_t* lut;                              /* [(N + 3) * 4] */
+    uint8_t* out;                                    /* [n_fields][ny*nx][4] */
+} rg_image;
+
+/* One 2-D product.  `out` receives n_fields planes of ny*nx elements, field-major (may be NULL when `image` is set:
+ * then only the RGBA image is written).  z indices are GLOBAL level indices (0..nz-1), inclusive. */
 typedef struct rg_product {
     int32_t kind;              /* rg_product_kind */
     int32_t mode;              /* rg_blend_mode (LEVEL); for BEAM: 0 = 'linear', 1 = 'nearest' */
@@ -174,6 +196,7 @@ typedef struct rg_product {
     double ke_re;              /* BEAM: ke * EARTH_RADIUS */
     double ke_re_sq;           /* BEAM: ke_re ** 2 */
     void* out;
+    const rg_image* image;     /* NULL, or the RGBA form of this product (not with partial) */
 } rg_product;
 
 /* Products of existing 3-D grids: n_fields grids of (z_end-z_begin)*ny*nx float32 each. */

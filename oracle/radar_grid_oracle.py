@@ -327,3 +327,65 @@ def grid_filter(kind, plane, a=None, b=None, fill_value=np.nan):
     else:
         raise ValueError(kind)
     return out
+
+
+# --------------------------------------------------------------------------------------------------
+# f4  RGBA image of a 2-D product      reference: src/radar_grid/geotiff.py:70-145
+# --------------------------------------------------------------------------------------------------
+
+def colormap_table(n=256):
+    """A deterministic (n + 3, 4) float table in matplotlib's ``Colormap._lut`` layout (n colours, then the under / over /
+    bad rows): test input only.  matplotlib is not installed where these tests run, so colour tables are inputs here."""
+    t = np.linspace(0.0, 1.0, n)
+    lut = np.stack([t, np.sin(np.pi * t) ** 2, 1.0 - t, np.full(n, 1.0)], axis=1)
+    return np.concatenate([lut, lut[:1], lut[-1:], np.zeros((1, 4))])
+
+
+def apply_colormap(data, lut, vmin=None, vmax=None, fill_value=None):
+    """
+    geotiff.py:105-143 with matplotlib's own steps written out (parity UNPINNED for the matplotlib half: the package is
+    absent from both containers, so Normalize / Colormap.__call__ are restated from matplotlib 3.8-3.10's sources):
+
+      nodata = (data == fill_value) if fill_value is not None else isnan(data)            geotiff.py:112-116
+      vmin / vmax default to nanmin / nanmax of the valid pixels, 0 / 1 if there are none  geotiff.py:118-129
+      Normalize(vmin, vmax, clip=True)(data): process_value keeps float32 data float32, but np.clip against the
+        float64 limits promotes to float64 (NEP 50), so x = (clip(data) - vmin) / (vmax - vmin) in float64;
+        vmin == vmax -> 0; vmin > vmax -> ValueError                                      colors.py Normalize.__call__
+      Colormap.__call__: xa = x * N; xa[xa == N] = N - 1; under = xa < 0; over = xa >= N; bad = isnan(xa);
+        xa.astype(int) (truncation); rgba = lut.take(xa)                                  colors.py Colormap.__call__
+      (rgba * 255).astype(uint8); alpha = 0 where nodata                                  geotiff.py:137-141
+
+    ``lut`` is the (N + 3, 4) float table (Colormap._lut).
+    """
+    data = np.array(data, copy=True)
+    lut = np.asarray(lut, dtype=np.float64)
+    n = lut.shape[0] - 3
+    nodata = (data == fill_value) if fill_value is not None else np.isnan(data)
+    valid = data[~nodata]
+    if len(valid) > 0:
+        if vmin is None:
+            vmin = np.nanmin(valid)
+        if vmax is None:
+            vmax = np.nanmax(valid)
+    else:
+        vmin = 0.0 if vmin is None else vmin
+        vmax = 1.0 if vmax is None else vmax
+    vmin64, vmax64 = np.float64(vmin), np.float64(vmax)
+    if vmin64 > vmax64:
+        raise ValueError("minvalue must be less than or equal to maxvalue")
+    if vmin64 == vmax64:
+        x = np.zeros(data.shape, dtype=data.dtype)
+    else:
+        x = np.clip(data, vmin64, vmax64)          # float64 result
+        x -= vmin64
+        x /= (vmax64 - vmin64)
+    xa = np.array(x, copy=True)
+    xa *= n
+    xa[xa == n] = n - 1
+    under, over, bad = xa < 0, xa >= n, np.isnan(xa)
+    with np.errstate(invalid="ignore"):
+        idx = xa.astype(int)
+    idx[under], idx[over], idx[bad] = n, n + 1, n + 2
+    rgba = (lut.take(idx, axis=0, mode="clip") * 255).astype(np.uint8)
+    rgba[nodata, 3] = 0
+    return rgba

@@ -170,10 +170,92 @@ int upload_axes(Context* ctx, Geometry* g)
 
 // Translate the public product list into the kernel parameter block.  `x_ax`/`y_ax` are device axes.
 // `plane_ptrs[i]` (device) replaces products[i].out when non-null (host-memspace staging).
+// Device-side placement of the image products of one call: LUT and RGBA output per product (nullptr = no image).
+struct ImageStage {
+    std::vector<const uchar4*> lut;
+    std::vector<uchar4*> out;
+};
+
+int check_image(const rg_product& pr)
+{
+    const rg_image& im = *pr.image;
+    if (pr.partial) return fail(RG_ERR_INVALID, "a partial (z-slab term) product has no image form");
+    if (im.n_filters < 0 || im.n_filters > RG_MAX_IMAGE_FILTERS) return fail(RG_ERR_INVALID, "image: n_filters must be 0..4");
+    for (int i = 0; i < im.n_filters; ++i)
+        if (im.filter_kind[i] < RG_PF_BELOW || im.filter_kind[i] > RG_PF_INVALID) return fail(RG_ERR_INVALID, "image: unknown filter kind");
+    if (!isfinite(im.vmin) || !isfinite(im.vmax)) return fail(RG_ERR_INVALID, "image: vmin and vmax must be finite");
+    if (im.vmin > im.vmax) return fail(RG_ERR_INVALID, "minvalue must be less than or equal to maxvalue");   // Normalize's ValueError
+    if (im.lut_entries < 1 || im.lut_entries > 4096) return fail(RG_ERR_INVALID, "image: lut_entries must be 1..4096");
+    if (!im.lut || !im.out) return fail(RG_ERR_INVALID, "image: lut / out pointer is NULL");
+    return RG_OK;
+}
+
+// Stage the LUTs (and, for host callers, device buffers for the RGBA planes) of the image products.
+int stage_images(Context* ctx, int n_products, const rg_product* products, bool host, int n_fields, int64_t ncol, ImageStage* st)
+{
+    st->lut.assign(std::max(n_products, 0), nullptr);
+    st->out.assign(std::max(n_products, 0), nullptr);
+    size_t lut_bytes = 0, out_bytes = 0;
+    int n_images = 0;
+    for (int i = 0; i < n_products; ++i) {
+        if (!products[i].image) continue;
+        RG_TRY(check_image(products[i]));
+        if (++n_images > RG_MAX_IMAGES) return fail(RG_ERR_UNSUPPORTED, "at most 3 image products per call");
+        lut_bytes += (((size_t)products[i].image->lut_entries + 3) * 4 + 255) & ~(size_t)255;
+        out_bytes += (((size_t)n_fields * (size_t)ncol * 4) + 255) & ~(size_t)255;
+    }
+    if (n_images == 0 || !host) {
+        for (int i = 0; i < n_products; ++i)
+            if (products[i].image) { st->lut[i] = (const uchar4*)products[i].image->lut; st->out[i] = (uchar4*)products[i].image->out; }
+        return RG_OK;
+    }
+    RG_TRY(ensure(ctx, ctx->luts, lut_bytes + out_bytes));
+    char* cur = (char*)ctx->luts.ptr;
+    for (int i = 0; i < n_products; ++i) {
+        if (!products[i].image) continue;
+        const size_t nb = ((size_t)products[i].image->lut_entries + 3) * 4;
+        RG_CUDA(cudaMemcpyAsync(cur, products[i].image->lut, nb, cudaMemcpyHostToDevice, ctx->stream));
+        st->lut[i] = (const uchar4*)cur;
+        cur += (nb + 255) & ~(size_t)255;
+    }
+    for (int i = 0; i < n_products; ++i) {
+        if (!products[i].image) continue;
+        st->out[i] = (uchar4*)cur;
+        cur += (((size_t)n_fields * (size_t)ncol * 4) + 255) & ~(size_t)255;
+    }
+    return RG_OK;
+}
+
+int fetch_images(Context* ctx, int n_products, const rg_product* products, int n_fields, int64_t ncol, const ImageStage& st)
+{
+    for (int i = 0; i < n_products; ++i)
+        if (products[i].image)
+            RG_CUDA(cudaMemcpyAsync(products[i].image->out, st.out[i], (size_t)n_fields * (size_t)ncol * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    return RG_OK;
+}
+
 int make_product_params(const rg_grid_spec& gs, int n_products, const rg_product* products, const float* x_ax,
-                        const float* y_ax, void* const* plane_ptrs, ProductParams* pp, int* z_need_lo, int* z_need_hi)
+                        const float* y_ax, void* const* plane_ptrs, const ImageStage* images, ProductParams* pp,
+                        int* z_need_lo, int* z_need_hi)
 {
     memset(pp, 0, sizeof(*pp));
+    pp->cmax_image = pp->cmin_image = pp->cmean_image = -1;
+    auto add_image = [&](int i) -> int {
+        const rg_product& pr = products[i];
+        if (!pr.image || !images) return -1;
+        const rg_image& im = *pr.image;
+        ImageParams& ip = pp->images[pp->n_images];
+        ip.on = 1;
+        ip.n_filters = im.n_filters;
+        for (int k = 0; k < RG_MAX_IMAGE_FILTERS; ++k) {
+            ip.kind[k] = im.filter_kind[k]; ip.a[k] = im.filter_a[k]; ip.b[k] = im.filter_b[k]; ip.fill[k] = im.filter_fill[k];
+        }
+        ip.vmin = im.vmin; ip.vmax = im.vmax; ip.fill_value = im.fill_value;
+        ip.has_fill = im.has_fill_value; ip.lut_n = im.lut_entries;
+        ip.lut = images->lut[i];
+        ip.out = images->out[i];
+        return pp->n_images++;
+    };
     pp->nz_full = gs.nz;
     pp->own_z0 = gs.z_begin;
     pp->own_z1 = gs.z_end;
@@ -188,25 +270,28 @@ int make_product_params(const rg_grid_spec& gs, int n_products, const rg_product
     if (n_products > 0 && products == nullptr) return fail(RG_ERR_INVALID, "products is NULL");
     for (int i = 0; i < n_products; ++i) {
         const rg_product& pr = products[i];
-        void* out = plane_ptrs ? plane_ptrs[i] : pr.out;
-        if (out == nullptr) return fail(RG_ERR_INVALID, "product output pointer is NULL");
+        void* out = pr.out == nullptr ? nullptr : (plane_ptrs ? plane_ptrs[i] : pr.out);
+        if (out == nullptr && !pr.image) return fail(RG_ERR_INVALID, "product output pointer is NULL");
         const int z0 = std::max(0, pr.z_lo), z1 = std::min(gs.nz - 1, pr.z_hi);
         switch (pr.kind) {
             case RG_PROD_COLMAX:
                 if (pp->cmax_on) return fail(RG_ERR_UNSUPPORTED, "at most one COLMAX per call");
                 pp->cmax_on = 1; pp->cmax_z0 = z0; pp->cmax_z1 = z1; pp->cmax_out = (float*)out;
                 pp->cmax_partial = pr.partial != 0;
+                pp->cmax_image = add_image(i);
                 lo = std::min(lo, z0); hi = std::max(hi, z1);
                 break;
             case RG_PROD_COLMIN:
                 if (pp->cmin_on) return fail(RG_ERR_UNSUPPORTED, "at most one COLMIN per call");
                 pp->cmin_on = 1; pp->cmin_z0 = z0; pp->cmin_z1 = z1; pp->cmin_out = (float*)out;
                 pp->cmin_partial = pr.partial != 0;
+                pp->cmin_image = add_image(i);
                 lo = std::min(lo, z0); hi = std::max(hi, z1);
                 break;
             case RG_PROD_COLMEAN:
                 if (pp->cmean_on) return fail(RG_ERR_UNSUPPORTED, "at most one COLMEAN per call");
                 pp->cmean_on = 1; pp->cmean_z0 = z0; pp->cmean_z1 = z1; pp->cmean_out = (float*)out;
+                pp->cmean_image = add_image(i);
                 lo = std::min(lo, z0); hi = std::max(hi, z1);
                 break;
             case RG_PROD_LEVEL:
@@ -217,6 +302,7 @@ int make_product_params(const rg_grid_spec& gs, int n_products, const rg_product
                 s.mode = pr.mode;
                 s.partial = pr.partial != 0;
                 s.out = out;
+                s.image = add_image(i);
                 if (pr.kind == RG_PROD_LEVEL) {
                     if (pr.mode < RG_BLEND_PICK || pr.mode > RG_BLEND_F64_OUT64) return fail(RG_ERR_INVALID, "bad blend mode");
                     if (pr.z_lo < 0 || pr.z_lo >= gs.nz || (pr.mode != RG_BLEND_PICK && (pr.z_hi < 0 || pr.z_hi >= gs.nz)))
@@ -346,7 +432,7 @@ int rg_context_destroy(rg_context* c)
     if (!ctx) return RG_OK;
     DeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (Scratch* s : {&ctx->records, &ctx->stage_in, &ctx->stage_out, &ctx->misc, &ctx->heavy})
+    for (Scratch* s : {&ctx->records, &ctx->stage_in, &ctx->stage_out, &ctx->misc, &ctx->heavy, &ctx->luts})
         if (s->ptr) cudaFree(s->ptr);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -754,15 +840,18 @@ int rg_products(rg_context* c, const rg_grid_spec* grid, int32_t n_fields, const
     }
     ProductParams pp;
     int zlo, zhi;
+    ImageStage images;
+    RG_TRY(stage_images(ctx, n_products, products, memspace == RG_HOST, n_fields, ncol, &images));
     RG_TRY(make_product_params(*grid, n_products, products, ax_dev, ax_dev + grid->nx,
-                               memspace == RG_HOST ? planes.data() : nullptr, &pp, &zlo, &zhi));
+                               memspace == RG_HOST ? planes.data() : nullptr, &images, &pp, &zlo, &zhi));
     RG_TRY(launch_products(ctx, *grid, n_fields, gdev, pp));
     if (memspace == RG_HOST) {
         for (int i = 0; i < n_products; ++i) {
-            if (!products[i].out) return fail(RG_ERR_INVALID, "product output pointer is NULL");
+            if (!products[i].out) continue;                 // image-only product
             RG_CUDA(cudaMemcpyAsync(products[i].out, planes[i], product_plane_bytes(products[i], n_fields, ncol),
                                     cudaMemcpyDeviceToHost, ctx->stream));
         }
+        RG_TRY(fetch_images(ctx, n_products, products, n_fields, ncol, images));
     }
     // xa/ya are stack-owned and host outputs must be complete on return
     RG_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -902,7 +991,9 @@ int rg_apply(rg_context* c, const rg_geometry* geom, const rg_apply_args* a, int
         if (dev_grid_tmp[f]) out_bytes += gbytes;
     }
     for (int i = 0; i < n_products; ++i)
-        if (!a->products || !a->products[i].out) return fail(RG_ERR_INVALID, "product output pointer is NULL");
+        if (!a->products || (!a->products[i].out && !a->products[i].image)) return fail(RG_ERR_INVALID, "product output pointer is NULL");
+    ImageStage images;
+    RG_TRY(stage_images(ctx, n_products, a->products, host, F, ncol, &images));
     if (host) {
         for (int i = 0; i < n_products; ++i) {
             plane_off[i] = out_bytes;
@@ -945,7 +1036,7 @@ int rg_apply(rg_context* c, const rg_geometry* geom, const rg_apply_args* a, int
     }
     int zlo = 0, zhi = -1;
     RG_TRY(make_product_params(g->grid, n_products, a->products, g->x_ax, g->y_ax, host ? planes.data() : nullptr,
-                               &ap.prod, &zlo, &zhi));
+                               &images, &ap.prod, &zlo, &zhi));
 
     if (ref_order) {
         // exact mode: un-fused.  Grid with NumPy's summation order, then the stand-alone product kernel.
@@ -974,8 +1065,10 @@ int rg_apply(rg_context* c, const rg_geometry* geom, const rg_apply_args* a, int
         for (int f = 0; f < F; ++f)
             if (want_grid[f]) RG_CUDA(cudaMemcpyAsync(a->grid_out[f], grid_dev[f], (size_t)V * 4, cudaMemcpyDeviceToHost, ctx->stream));
         for (int i = 0; i < n_products; ++i)
-            RG_CUDA(cudaMemcpyAsync(a->products[i].out, planes[i], product_plane_bytes(a->products[i], F, ncol),
-                                    cudaMemcpyDeviceToHost, ctx->stream));
+            if (a->products[i].out)
+                RG_CUDA(cudaMemcpyAsync(a->products[i].out, planes[i], product_plane_bytes(a->products[i], F, ncol),
+                                        cudaMemcpyDeviceToHost, ctx->stream));
+        RG_TRY(fetch_images(ctx, n_products, a->products, F, ncol, images));
         RG_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     return RG_OK;

@@ -205,6 +205,48 @@ __device__ __forceinline__ int clampi(double v, int lo, int hi)
     return (int)v;
 }
 
+// RGBA form of one finished product value (rg_image): GridFilter thresholds in the plane's own type (filters.py:660,
+// 689, 721, 746), then reference geotiff.py:122-143 with matplotlib's arithmetic: Normalize(vmin, vmax, clip=True) --
+// np.clip against the float64 limits promotes to float64, so clip, subtract and divide are float64 operations -- and
+// Colormap.__call__: xa = x * N, xa == N -> N - 1, NaN -> the "bad" row N + 2, astype(int) truncation.  The LUT rows are
+// already (lut * 255).astype(uint8); alpha is 0 for no-data pixels.
+template <typename T>
+__device__ __forceinline__ void emit_image(const ImageParams& im, size_t o, T v)
+{
+#pragma unroll
+    for (int i = 0; i < RG_MAX_IMAGE_FILTERS; ++i) {
+        if (i < im.n_filters) {
+            const T a = (T)im.a[i], b = (T)im.b[i];
+            bool hit;
+            switch (im.kind[i]) {
+                case RG_PF_BELOW: hit = v < a; break;
+                case RG_PF_ABOVE: hit = v > a; break;
+                case RG_PF_OUTSIDE: hit = (v < a) || (v > b); break;
+                default: hit = isnan(v) || isinf(v); break;
+            }
+            if (hit) v = (T)im.fill[i];
+        }
+    }
+    const bool nodata = im.has_fill ? (v == (T)im.fill_value) : isnan(v);
+    int idx;
+    if (isnan(v)) {
+        idx = im.lut_n + 2;
+    } else {
+        double x = 0.0;
+        if (im.vmin != im.vmax) {
+            const double d = (double)v;
+            const double c = d < im.vmin ? im.vmin : (d > im.vmax ? im.vmax : d);
+            x = __ddiv_rn(__dsub_rn(c, im.vmin), __dsub_rn(im.vmax, im.vmin));
+        }
+        double xa = __dmul_rn(x, (double)im.lut_n);
+        if (xa == (double)im.lut_n) xa = (double)(im.lut_n - 1);
+        idx = xa < 0.0 ? im.lut_n : (xa >= (double)im.lut_n ? im.lut_n + 1 : (int)xa);
+    }
+    uchar4 c = __ldg(im.lut + idx);
+    if (nodata) c.w = 0;
+    im.out[o] = c;
+}
+
 struct ColumnState {
     float cmax, cmin, msum;
     int mcnt;
@@ -361,11 +403,16 @@ struct ColumnState {
         const float qnan = __uint_as_float(kCanonNaN);
         // partial (z-slab) planes carry "no data in this slab" as the neutral element of the collective that follows:
         // -inf / +inf for all-reduce(MAX / MIN), -0.0 for all-reduce(SUM) (x + -0.0 == x for every x, signed zeros included)
-        if (pp.cmax_on) pp.cmax_out[o] = pp.cmax_partial && isnan(cmax) ? __uint_as_float(0xFF800000u) : cmax;
-        if (pp.cmin_on) pp.cmin_out[o] = pp.cmin_partial && isnan(cmin) ? __uint_as_float(0x7F800000u) : cmin;
+        auto put = [&](void* out, int image, auto val) {
+            using T = decltype(val);
+            if (out != nullptr) reinterpret_cast<T*>(out)[o] = val;
+            if (image >= 0) emit_image<T>(pp.images[image], o, val);
+        };
+        if (pp.cmax_on) put(pp.cmax_out, pp.cmax_image, pp.cmax_partial && isnan(cmax) ? __uint_as_float(0xFF800000u) : cmax);
+        if (pp.cmin_on) put(pp.cmin_out, pp.cmin_image, pp.cmin_partial && isnan(cmin) ? __uint_as_float(0x7F800000u) : cmin);
         if (pp.cmean_on) {
             // _divide_by_count: true_divide(float32 sum, intp count) evaluates in float64, stored as float32
-            pp.cmean_out[o] = (float)__ddiv_rn((double)msum, (double)mcnt);
+            put(pp.cmean_out, pp.cmean_image, (float)__ddiv_rn((double)msum, (double)mcnt));
         }
 #pragma unroll
         for (int k = 0; k < RG_MAX_SLICES; ++k) {
@@ -380,7 +427,7 @@ struct ColumnState {
                     if (s.mode == 1) {
                         const double zi = rint(zf);
                         const bool ok = zi >= 0.0 && zi < (double)pp.nz_full;
-                        reinterpret_cast<float*>(s.out)[o] = !ok ? qnan : own_lo ? s_lo[k] : -0.0f;   // products.py:263-272
+                        put(s.out, s.image, !ok ? qnan : own_lo ? s_lo[k] : -0.0f);                  // products.py:263-272
                     } else {
                         const double w_hi = __dsub_rn(zf, floor(zf));                      // products.py:287-288
                         const double w_lo = __dsub_rn(1.0, w_hi);
@@ -388,21 +435,21 @@ struct ColumnState {
                         const double t_hi = own_hi ? __dmul_rn(w_hi, (double)s_hi[k]) : -0.0;
                         double r = __dadd_rn(t_lo, t_hi);
                         if (tz < pp.z_min || tz > pp.z_max) r = (double)qnan;              // products.py:306-309
-                        reinterpret_cast<double*>(s.out)[o] = r;
+                        put(s.out, s.image, r);
                     }
                 } else if (s.mode == RG_BLEND_PICK) {
-                    reinterpret_cast<float*>(s.out)[o] = own_lo ? s_lo[k] : -0.0f;
+                    put(s.out, s.image, own_lo ? s_lo[k] : -0.0f);
                 } else if (s.mode == RG_BLEND_F32) {
                     const float t_lo = own_lo ? __fmul_rn((float)s.w_lo, s_lo[k]) : -0.0f;
                     const float t_hi = own_hi ? __fmul_rn((float)s.w_hi, s_hi[k]) : -0.0f;
-                    reinterpret_cast<float*>(s.out)[o] = __fadd_rn(t_lo, t_hi);
+                    put(s.out, s.image, __fadd_rn(t_lo, t_hi));
                 } else {
                     const double t_lo = own_lo ? __dmul_rn(s.w_lo, (double)s_lo[k]) : -0.0;
                     const double t_hi = own_hi ? __dmul_rn(s.w_hi, (double)s_hi[k]) : -0.0;
                     const double r = __dadd_rn(t_lo, t_hi);
                     // a partial float64 blend stays float64 until the ranks' terms have been added
-                    if (s.mode == RG_BLEND_F64_OUT64 || s.partial) reinterpret_cast<double*>(s.out)[o] = r;
-                    else reinterpret_cast<float*>(s.out)[o] = (float)r;
+                    if (s.mode == RG_BLEND_F64_OUT64 || s.partial) put(s.out, s.image, r);
+                    else put(s.out, s.image, (float)r);
                 }
             }
         }
@@ -1099,6 +1146,7 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
                     st.s_lo[0] = q_lo[k];
                     st.s_hi[0] = q_hi[k];
                 }
+                st.zz[0] = p.prod.slices[0].z_lo | (p.prod.slices[0].z_hi << 16);   // ownership test of a partial (z-slab) blend
                 st.write(p.prod, gl + k * W, col, p.ncol, 0.f, 0.f);   // only cmax and the LEVEL slice are on: x, y unused
             }
         }

@@ -115,6 +115,7 @@ struct Context {
     Scratch stage_in;                    // H2D staging of fields / masks / rule values
     Scratch stage_out;                   // device-side outputs of a host-memspace call
     Scratch misc;
+    Scratch luts;                        // colormap LUTs of the image products of a call
     Scratch heavy;                       // per-chunk partial sums of the heavy rows: float[n_heavy_chunks][2 * F]
 };
 
@@ -123,6 +124,19 @@ void timer_begin(Context* ctx, int which);
 void timer_end(Context* ctx, int which);
 
 // ---- kernel-facing parameter blocks -----------------------------------------------------------------
+constexpr int RG_MAX_IMAGES = 3;          // products of one call that also leave as RGBA images
+// RGBA form of a product plane (rg_image): thresholds, then the colormap index arithmetic of geotiff.py:70-145
+struct ImageParams {
+    int32_t on;
+    int32_t n_filters;
+    int32_t kind[RG_MAX_IMAGE_FILTERS];
+    double a[RG_MAX_IMAGE_FILTERS], b[RG_MAX_IMAGE_FILTERS], fill[RG_MAX_IMAGE_FILTERS];
+    double vmin, vmax, fill_value;
+    int32_t has_fill, lut_n;
+    const uchar4* lut;                    // device, lut_n + 3 entries
+    uchar4* out;                          // [n_fields][ncol]
+};
+
 struct SliceParams {                      // one RG_PROD_LEVEL / RG_PROD_BEAM product
     int32_t kind;                         // 0 = unused, RG_PROD_LEVEL, RG_PROD_BEAM
     int32_t mode;                         // LEVEL: rg_blend_mode.  BEAM: 0 linear, 1 nearest
@@ -132,6 +146,8 @@ struct SliceParams {                      // one RG_PROD_LEVEL / RG_PROD_BEAM pr
     double w_lo, w_hi;
     double sin_e, cos_c, tan_e, ke_re, ke_re_sq;
     void* out;
+    int32_t image;                        // index into ProductParams::images, -1 = none
+    int32_t pad_;
 };
 
 struct ProductParams {
@@ -147,6 +163,8 @@ struct ProductParams {
     float* cmax_out;
     float* cmin_out;
     float* cmean_out;
+    int32_t cmax_image, cmin_image, cmean_image, n_images;   // index into images, -1 = none
+    ImageParams images[RG_MAX_IMAGES];
     double z_min, z_max, z_step;
     const float* x_ax;
     const float* y_ax;

@@ -20,7 +20,8 @@ from .products import (EARTH_RADIUS, EFFECTIVE_RADIUS_FACTOR, column_max, column
                        compute_beam_height, compute_beam_height_flat, compute_beam_height_simple,
                        constant_altitude_ppi, constant_elevation_ppi, get_beam_height_difference,
                        get_elevation_from_z_level)
-from .engine import (CAPPI, PPI, LevelPick, ColumnMax, ColumnMean, ColumnMin, DeviceGeometry, GeometryCache, RangeRule, VolumePipeline, grid_fields,
+from .geotiff import apply_colormap_to_array
+from .engine import (ImageSpec, colormap_lut_bytes, CAPPI, PPI, LevelPick, ColumnMax, ColumnMean, ColumnMin, DeviceGeometry, GeometryCache, RangeRule, VolumePipeline, grid_fields,
                      run_products)
 
 __version__ = "0.1.0"
@@ -35,6 +36,7 @@ __all__ = [
     "compute_beam_height_flat", "compute_beam_height_simple", "EARTH_RADIUS", "EFFECTIVE_RADIUS_FACTOR",
     # engine-level API
     "DeviceGeometry", "grid_fields", "run_products", "RangeRule", "VolumePipeline", "GeometryCache",
-    "ColumnMax", "ColumnMin", "ColumnMean", "CAPPI", "PPI", "LevelPick",
+    "ColumnMax", "ColumnMin", "ColumnMean", "CAPPI", "PPI", "LevelPick", "ImageSpec", "colormap_lut_bytes",
+    "apply_colormap_to_array",
     "set_device", "get_device", "pinned_empty",
 ]

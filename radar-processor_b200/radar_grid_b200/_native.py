@@ -40,12 +40,23 @@ class GeometryInfo(C.Structure):
                 ("build_ms", C.c_double), ("cell_size", C.c_double), ("grid", GridSpec)]
 
 
+RG_MAX_IMAGE_FILTERS = 4
+
+
+class Image(C.Structure):
+    _fields_ = [("n_filters", C.c_int32), ("filter_kind", C.c_int32 * RG_MAX_IMAGE_FILTERS),
+                ("filter_a", C.c_double * RG_MAX_IMAGE_FILTERS), ("filter_b", C.c_double * RG_MAX_IMAGE_FILTERS),
+                ("filter_fill", C.c_double * RG_MAX_IMAGE_FILTERS), ("vmin", C.c_double), ("vmax", C.c_double),
+                ("fill_value", C.c_double), ("has_fill_value", C.c_int32), ("lut_entries", C.c_int32),
+                ("lut", C.c_void_p), ("out", C.c_void_p)]
+
+
 class Product(C.Structure):
     _fields_ = [("kind", C.c_int32), ("mode", C.c_int32), ("z_lo", C.c_int32), ("z_hi", C.c_int32),
                 ("earth_curvature", C.c_int32), ("partial", C.c_int32),
                 ("w_lo", C.c_double), ("w_hi", C.c_double), ("sin_elev", C.c_double),
                 ("cos_elev_clamped", C.c_double), ("tan_elev", C.c_double), ("ke_re", C.c_double),
-                ("ke_re_sq", C.c_double), ("out", C.c_void_p)]
+                ("ke_re_sq", C.c_double), ("out", C.c_void_p), ("image", C.POINTER(Image))]
 
 
 class QcRule(C.Structure):
@@ -134,7 +145,7 @@ def lib():
             fn = getattr(handle, name)       # AttributeError here = header / library mismatch
             fn.restype = restype
             fn.argtypes = argtypes
-        if handle.rg_abi_version() != 1:
+        if handle.rg_abi_version() != 2:
             raise RuntimeError("libradargrid_b200.so ABI version mismatch")
         _lib = handle
         return _lib

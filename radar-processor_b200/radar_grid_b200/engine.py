@@ -197,6 +197,79 @@ def resolve_z_limits(nz, grid_limits, z_min_idx=None, z_max_idx=None, z_min_alt=
     return max(0, int(z_min_idx)), min(nz - 1, int(z_max_idx))
 
 
+def colormap_lut_bytes(cmap) -> np.ndarray:
+    """
+    (N + 3, 4) uint8 table the image epilogue indexes: rows 0..N-1 the colours, then matplotlib's under / over / bad
+    rows, each ``(lut * 255).astype(uint8)`` exactly as reference geotiff.py:137 scales the colormap's output.
+
+    ``cmap`` may be a matplotlib Colormap (its ``_lut`` is used), a colormap name (needs matplotlib), or an array: float
+    in [0, 1] or uint8, with N rows (under / over default to the first / last colour, bad to transparent black, as
+    matplotlib's defaults) or N + 3 rows when ``cmap`` is a ``(table, "with_extremes")`` tuple.
+    """
+    with_ext = False
+    if isinstance(cmap, tuple) and len(cmap) == 2 and cmap[1] == "with_extremes":
+        cmap, with_ext = cmap[0], True
+    if isinstance(cmap, str):
+        try:
+            import matplotlib.pyplot as plt
+        except ImportError as e:                            # the reference calls plt.get_cmap(cmap) (geotiff.py:106-107)
+            raise ImportError("colormap names need matplotlib; pass the colormap's table (an (N, 4) array) instead") from e
+        cmap = plt.get_cmap(cmap)
+    if hasattr(cmap, "_lut") and hasattr(cmap, "N"):
+        if not getattr(cmap, "_isinit", True):
+            cmap._init()
+        table, with_ext = np.asarray(cmap._lut), True
+    else:
+        table = np.asarray(cmap)
+    if table.ndim != 2 or table.shape[1] != 4:
+        raise ValueError("colormap table must have shape (N, 4) or (N + 3, 4)")
+    if table.dtype != np.uint8:
+        table = (table.astype(np.float64) * 255).astype(np.uint8)
+    if not with_ext:
+        table = np.concatenate([table, table[:1], table[-1:], np.zeros((1, 4), np.uint8)])
+    if table.shape[0] < 4:
+        raise ValueError("colormap table needs at least one colour")
+    return np.ascontiguousarray(table)
+
+
+@dataclass
+class ImageSpec:
+    """RGBA form of a 2-D product, produced by the epilogue that finishes the product (rg_image): GridFilter thresholds
+    (reference filters.py:631-746; ``filters`` = [("below", thr, fill) | ("above", thr, fill) | ("outside", lo, hi, fill)
+    | ("invalid", fill)], applied in order), then reference geotiff.py:70-145 ``apply_colormap_to_array`` with explicit
+    vmin / vmax.  ``keep_plane=False`` drops the float plane: only ny*nx*4 bytes per field leave the GPU."""
+    cmap: object
+    vmin: float
+    vmax: float
+    fill_value: Optional[float] = None
+    filters: Sequence[tuple] = ()
+    keep_plane: bool = True
+
+    def struct(self, lut_ptr: int, n_entries: int, out_ptr: int) -> "N.Image":
+        if self.vmin > self.vmax:
+            raise ValueError("minvalue must be less than or equal to maxvalue")
+        if len(self.filters) > N.RG_MAX_IMAGE_FILTERS:
+            raise ValueError(f"at most {N.RG_MAX_IMAGE_FILTERS} grid filters per image")
+        im = N.Image()
+        im.n_filters = len(self.filters)
+        for i, f in enumerate(self.filters):
+            kind = {"below": N.RG_PF_BELOW, "above": N.RG_PF_ABOVE, "outside": N.RG_PF_OUTSIDE, "invalid": N.RG_PF_INVALID}[f[0]]
+            im.filter_kind[i] = kind
+            if kind == N.RG_PF_OUTSIDE:
+                im.filter_a[i], im.filter_b[i], im.filter_fill[i] = float(f[1]), float(f[2]), float(f[3]) if len(f) > 3 else np.nan
+            elif kind == N.RG_PF_INVALID:
+                im.filter_fill[i] = float(f[1]) if len(f) > 1 else np.nan
+            else:
+                im.filter_a[i], im.filter_fill[i] = float(f[1]), float(f[2]) if len(f) > 2 else np.nan
+        im.vmin, im.vmax = float(self.vmin), float(self.vmax)
+        im.has_fill_value = int(self.fill_value is not None)
+        im.fill_value = 0.0 if self.fill_value is None else float(self.fill_value)
+        im.lut_entries = n_entries
+        im.lut = lut_ptr
+        im.out = out_ptr
+        return im
+
+
 @dataclass
 class ColumnMax:
     z_min_idx: Optional[int] = None
@@ -204,6 +277,7 @@ class ColumnMax:
     z_min_alt: Optional[float] = None
     z_max_alt: Optional[float] = None
     partial: bool = False      # z-slab term: "no data in this slab" is -inf (+inf for ColumnMin), see distributed.zslab_products
+    image: Optional[ImageSpec] = None
     kind = N.RG_PROD_COLMAX
     name = "column_max"
 
@@ -240,6 +314,7 @@ class CAPPI:
     altitude: float
     interpolation: str = "linear"
     partial: bool = False      # z-slab term of the blend (sum over the owned levels of weight * level), see distributed.zslab_products
+    image: Optional[ImageSpec] = None
     name = "cappi"
 
     def resolve(self, grid_shape, grid_limits, have_geometry=True):
@@ -289,6 +364,7 @@ class LevelPick:
     z-slab contributes to a CAPPI whose two levels live in different slabs (distributed.cappi_zslab)."""
     level: int
     partial: bool = False      # z-slab term: the level where the slab owns it, -0.0 elsewhere
+    image: Optional[ImageSpec] = None
     name = "level"
 
     def resolve(self, grid_shape, grid_limits, have_geometry=True):
@@ -305,6 +381,7 @@ class PPI:
     earth_curvature: bool = True
     ke: float = EFFECTIVE_RADIUS_FACTOR
     partial: bool = False      # z-slab term of the per-pixel blend, see distributed.zslab_products
+    image: Optional[ImageSpec] = None
     name = "ppi"
 
     def resolve(self, grid_shape, grid_limits, have_geometry=True):
@@ -355,9 +432,44 @@ def _fill_nan(x, device):
         x.fill(np.nan)
 
 
+def _attach_image(request, pr, device: bool, F: int, ny: int, nx: int, ref, keep: list):
+    """Allocate the RGBA output of an image request, stage its LUT and hook both onto the product struct."""
+    spec = getattr(request, "image", None)
+    if spec is None or pr is None:
+        return None
+    table = colormap_lut_bytes(spec.cmap)
+    if device:
+        import torch
+        lut = torch.from_numpy(table).to(ref.device)
+        out = torch.empty((F, ny, nx, 4), dtype=torch.uint8, device=ref.device)
+    else:
+        lut, out = table, np.empty((F, ny, nx, 4), dtype=np.uint8)
+    im = spec.struct(_ptr(lut, device), table.shape[0] - 3, _ptr(out, device))
+    pr.image = C.pointer(im)
+    keep += [lut, im]
+    return out
+
+
+def _nodata_image(request, device: bool, F: int, ny: int, nx: int, ref):
+    """Image of an all-NaN plane (a CAPPI outside the grid): every pixel is the colormap's "bad" entry."""
+    spec = getattr(request, "image", None)
+    if spec is None:
+        return None
+    table = colormap_lut_bytes(spec.cmap)
+    px = table[-1].copy()
+    if spec.fill_value is None:
+        px[3] = 0                                            # NaN is the no-data value: transparent
+    img = np.broadcast_to(px, (F, ny, nx, 4)).copy()
+    if device:
+        import torch
+        return torch.from_numpy(img).to(ref.device)
+    return img
+
+
 def run_products(grids: Sequence, grid_shape, grid_limits, products: Sequence, z_range=None,
-                 ctx: Optional[N.Context] = None, have_geometry=True) -> List:
-    """Stand-alone K6 on existing 3-D grids (NumPy or torch CUDA float32, shape slab x ny x nx)."""
+                 ctx: Optional[N.Context] = None, have_geometry=True, with_images: bool = False):
+    """Stand-alone K6 on existing 3-D grids (NumPy or torch CUDA float32, shape slab x ny x nx).  With ``with_images``
+    the return value is ``(planes, images)``: images[i] is the (F, ny, nx, 4) uint8 RGBA form of request i or None."""
     ctx = ctx or N.default_context()
     device = N.is_device_array(grids[0])
     F = len(grids)
@@ -371,14 +483,18 @@ def run_products(grids: Sequence, grid_shape, grid_limits, products: Sequence, z
     for g in held:
         if int(np.prod(g.shape)) != n_rows:
             raise ValueError(f"grid has {int(np.prod(g.shape))} voxels, expected {n_rows}")
-    outs, structs = [], []
+    outs, structs, images, keep = [], [], [], []
     for p in products:
         pr, dt = p.resolve(grid_shape, grid_limits, have_geometry)
-        out = _alloc_like(device, (F, ny, nx), dt, held[0])
+        img_spec = getattr(p, "image", None)
+        out = None if (img_spec is not None and not img_spec.keep_plane) else _alloc_like(device, (F, ny, nx), dt, held[0])
         if pr is None:
-            _fill_nan(out, device)
+            if out is not None:
+                _fill_nan(out, device)
+            images.append(_nodata_image(p, device, F, ny, nx, held[0]))
         else:
-            pr.out = _ptr(out, device)
+            pr.out = None if out is None else _ptr(out, device)
+            images.append(_attach_image(p, pr, device, F, ny, nx, held[0], keep))
             structs.append(pr)
         outs.append(out)
     if structs:
@@ -387,7 +503,8 @@ def run_products(grids: Sequence, grid_shape, grid_limits, products: Sequence, z
         with N.torch_stream_order(ctx, device):
             N.check(N.lib().rg_products(ctx.handle, C.byref(spec), F, gp, len(structs), arr,
                                         N.RG_DEVICE if device else N.RG_HOST))
-    return outs
+    del keep
+    return (outs, images) if with_images else outs
 
 
 def grid_fields(geom: DeviceGeometry, fields: Sequence, masks: Optional[Sequence] = None,
@@ -407,7 +524,8 @@ def grid_fields(geom: DeviceGeometry, fields: Sequence, masks: Optional[Sequence
     products      ColumnMax / ColumnMin / ColumnMean / CAPPI / PPI requests, fused in the epilogue
     out_grids / out_products  optional preallocated outputs (e.g. pinned host arrays) of the right shape/dtype
 
-    Returns {"grids": [array or None per field], "products": [array (F, ny, nx) per request]}.
+    Returns {"grids": [array or None per field], "products": [array (F, ny, nx) per request, None for an image-only
+    request], "images": [uint8 array (F, ny, nx, 4) per request with an ``image`` spec, else None]}.
     """
     ctx = ctx or geom.ctx
     F = len(fields)
@@ -473,17 +591,23 @@ def grid_fields(geom: DeviceGeometry, fields: Sequence, masks: Optional[Sequence
     if len(rstructs) > N.RG_MAX_RULES:
         raise ValueError(f"at most {N.RG_MAX_RULES} fused range rules per pass")
 
-    pouts, pstructs = [], []
+    pouts, pstructs, pimages, ikeep = [], [], [], []
     for k, p in enumerate(products):
         pr, dt = p.resolve(geom.grid_shape, geom.grid_limits, True)
+        img_spec = getattr(p, "image", None)
         if out_products is not None and out_products[k] is not None:
             out = out_products[k]
+        elif img_spec is not None and not img_spec.keep_plane:
+            out = None
         else:
             out = _alloc_like(device, (F, ny, nx), dt, fheld[0])
         if pr is None:
-            _fill_nan(out, device)
+            if out is not None:
+                _fill_nan(out, device)
+            pimages.append(_nodata_image(p, device, F, ny, nx, fheld[0]))
         else:
-            pr.out = _ptr(out, device)
+            pr.out = None if out is None else _ptr(out, device)
+            pimages.append(_attach_image(p, pr, device, F, ny, nx, fheld[0], ikeep))
             pstructs.append(pr)
         pouts.append(out)
 
@@ -506,7 +630,7 @@ def grid_fields(geom: DeviceGeometry, fields: Sequence, masks: Optional[Sequence
     args.products = parr
     with N.torch_stream_order(ctx, device):
         N.check(N.lib().rg_apply(ctx.handle, geom._h, C.byref(args), N.RG_DEVICE if device else N.RG_HOST))
-    return {"grids": grids, "products": pouts, "_keep": (fheld, mheld, rheld)}
+    return {"grids": grids, "products": pouts, "images": pimages, "_keep": (fheld, mheld, rheld, ikeep)}
 
 
 class GeometryCache:

@@ -30,11 +30,11 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), f"{name} is declared in the header but not exported"
     assert sorted(N._PROTOTYPES) == names, "ctypes prototypes and header declarations differ"
-    assert lib.rg_abi_version() == 1
+    assert lib.rg_abi_version() == 2
 
 
 def test_struct_layouts_match_the_c_compiler(tmp_path):
-    structs = {"rg_grid_spec": N.GridSpec, "rg_geometry_info": N.GeometryInfo, "rg_product": N.Product,
+    structs = {"rg_grid_spec": N.GridSpec, "rg_geometry_info": N.GeometryInfo, "rg_product": N.Product, "rg_image": N.Image,
                "rg_qc_rule": N.QcRule, "rg_apply_args": N.ApplyArgs}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "radar_grid_b200.h"', "int main(void) {"]
     for cname, ct in structs.items():

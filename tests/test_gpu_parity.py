@@ -544,7 +544,8 @@ def test_zslab_fused_terms_of_every_product_kind_merge_to_the_unsharded_products
                     rg.CAPPI(1234.5, "nearest"), rg.PPI(2.3)]
             reqs2 = [rg.ColumnMax(z_max_idx=nz - 2), rg.PPI(6.9, "nearest"), rg.PPI(0.5, earth_curvature=False), rg.LevelPick(nz - 1),
                      rg.CAPPI(spec.grid_limits[0][1] + 10.0)]
-            for rq in (reqs, reqs2):
+            reqs3 = [rg.ColumnMax(), rg.CAPPI((ranges[0][1] - 0.6) * step)]     # the operational pair: its own kernel variant
+            for rq in (reqs, reqs2, reqs3):
                 whole.grid_limits = lims
                 want = rg.grid_fields(whole, data, masks=masks, want_grid=False, products=rq)["products"]
                 acc = None

@@ -205,3 +205,69 @@ def test_grid_filter_thresholds(impl):
     h = np.array([[10.0, np.nan, 30.0], [15.0, np.inf, 35.0]], dtype=np.float32)
     r = impl.gridfilter("invalid", h, fill_value=-99.0)
     assert r[0, 1] == -99.0 and r[1, 1] == -99.0 and r[0, 0] == 10.0 and r.dtype == np.float32
+
+
+# ---- RGBA image of a product (geotiff.py:70-145) -------------------------------------------------------------------
+def test_oracle_colormap_index_arithmetic_known_answers():
+    """Hand-checked indices of the colour table: vmin -> entry 0, vmax -> the LAST entry (x == 1 is not 'over'), values
+    outside [vmin, vmax] clip, NaN -> the 'bad' row with alpha 0, fill_value pixels keep their colour but alpha 0."""
+    lut = O.colormap_table(4)                       # 4 colours + under / over / bad
+    b = (lut * 255).astype(np.uint8)
+    data = np.array([[0.0, 10.0, 2.4, 2.5, 7.49, 7.5, -5.0, 50.0, np.nan, 9.999]], dtype=np.float32)
+    got = O.apply_colormap(data, lut, vmin=0.0, vmax=10.0)
+    want_idx = [0, 3, 0, 1, 2, 3, 0, 3, 6, 3]
+    for k, i in enumerate(want_idx):
+        exp = b[i].copy()
+        if k == 8:
+            exp[3] = 0
+        np.testing.assert_array_equal(got[0, k], exp, err_msg=f"pixel {k}")
+    got = O.apply_colormap(data, lut, vmin=0.0, vmax=10.0, fill_value=10.0)
+    assert got[0, 1, 3] == 0 and np.array_equal(got[0, 1, :3], b[3, :3]) and got[0, 8, 3] == b[6, 3]
+    np.testing.assert_array_equal(O.apply_colormap(data, lut, vmin=3.0, vmax=3.0)[0, :8], np.broadcast_to(b[0], (8, 4)))
+    auto = O.apply_colormap(data, lut)               # vmin = -5, vmax = 50 from the valid data
+    assert np.array_equal(auto[0, 6], b[0]) and np.array_equal(auto[0, 7], b[3])
+    with pytest.raises(ValueError):
+        O.apply_colormap(data, lut, vmin=2.0, vmax=1.0)
+
+
+@pytest.mark.gpu
+def test_cuda_image_epilogue_matches_the_colormap_restatement_and_gridfilter():
+    """The fused image epilogue (GridFilter thresholds, then the colormap) on the CUDA path: the same bytes as
+    oracle.apply_colormap applied to the oracle's GridFilter output, for float32 planes (COLMAX, CAPPI), the float64
+    PPI plane, an explicit fill_value, and an image-only request (no float plane leaves the device)."""
+    from conftest import golden_case
+    spec, radar, gates, fields, g = golden_case("tiny")
+    geom = rg.GridGeometry(spec.grid_shape, spec.grid_limits, g["indptr"], g["gate_indices"], g["weights"], float(g["toa"][0]))
+    dev = geom.device_geometry(n_gates=spec.n_gates)
+    lut = O.colormap_table(256)
+    dbz = fields["DBZH"]
+    table = (lut, "with_extremes")                  # N + 3 rows: the colours plus matplotlib's under / over / bad rows
+    img = rg.ImageSpec(table, -10.0, 60.0, filters=[("below", 5.0, np.nan), ("above", 45.0, 45.0)])
+    img_fill = rg.ImageSpec(table, 0.0, 50.0, fill_value=-999.0, filters=[("invalid", -999.0), ("outside", 0.0, 40.0, -999.0)],
+                            keep_plane=False)
+    res = rg.grid_fields(dev, [np.ma.getdata(dbz)], masks=[np.ma.getmaskarray(dbz)], reference_order=True,
+                         products=[rg.ColumnMax(image=img), rg.CAPPI(1234.5, image=img_fill), rg.PPI(2.3, image=img)])
+    colmax, cappi_plane, ppi = res["products"]
+    assert cappi_plane is None and res["images"][1].shape == (1,) + spec.grid_shape[1:] + (4,)
+    np.testing.assert_array_equal(colmax[0], g["colmax"])
+    f = O.grid_filter("above", O.grid_filter("below", g["colmax"], 5.0), 45.0, fill_value=45.0)
+    np.testing.assert_array_equal(res["images"][0][0], O.apply_colormap(f, lut, -10.0, 60.0))
+    cap = g["cappi_lin_1234.5"]
+    f = O.grid_filter("outside", O.grid_filter("invalid", cap, fill_value=-999.0), 0.0, 40.0, fill_value=-999.0)
+    np.testing.assert_array_equal(res["images"][1][0], O.apply_colormap(f, lut, 0.0, 50.0, fill_value=-999.0))
+    f = O.grid_filter("above", O.grid_filter("below", g["ppi_lin_2.3"], 5.0), 45.0, fill_value=45.0)
+    assert ppi.dtype == np.float64
+    np.testing.assert_array_equal(res["images"][2][0], O.apply_colormap(f, lut, -10.0, 60.0))
+    # the fast fused path gives the same image wherever its plane equals the exact one (thresholds may flip a pixel that
+    # sits within the fast path's 1e-5 of a threshold, so compare through the plane it actually produced)
+    fast = rg.grid_fields(dev, [np.ma.getdata(dbz)], masks=[np.ma.getmaskarray(dbz)], want_grid=False, products=[rg.ColumnMax(image=img)])
+    f = O.grid_filter("above", O.grid_filter("below", fast["products"][0][0], 5.0), 45.0, fill_value=45.0)
+    np.testing.assert_array_equal(fast["images"][0][0], O.apply_colormap(f, lut, -10.0, 60.0))
+    # the reference-shaped function on a finished plane, default vmin / vmax
+    np.testing.assert_array_equal(rg.apply_colormap_to_array(g["colmax"], table), O.apply_colormap(g["colmax"], lut))
+    np.testing.assert_array_equal(rg.apply_colormap_to_array(g["colmax"], lut[:256]), O.apply_colormap(g["colmax"], lut))   # default extremes
+    np.testing.assert_array_equal(rg.apply_colormap_to_array(g["colmax"], table, vmin=0.0, vmax=30.0, fill_value=float(np.nanmax(g["colmax"]))),
+                                  O.apply_colormap(g["colmax"], lut, 0.0, 30.0, fill_value=float(np.nanmax(g["colmax"]))))
+    oob = rg.grid_fields(dev, [np.ma.getdata(dbz)], masks=[np.ma.getmaskarray(dbz)], want_grid=False,
+                         products=[rg.CAPPI(1e6, image=img)])                 # outside the grid: all no-data
+    np.testing.assert_array_equal(oob["images"][0][0], O.apply_colormap(np.full(spec.grid_shape[1:], np.nan, np.float32), lut, -10.0, 60.0))

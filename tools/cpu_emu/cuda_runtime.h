@@ -29,6 +29,7 @@ struct uint2 { unsigned x, y; };
 struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
 struct uint3 { unsigned x, y, z; };
+struct uchar4 { unsigned char x, y, z, w; };
 struct dim3 {
     unsigned x, y, z;
     dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
