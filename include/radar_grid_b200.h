@@ -105,6 +105,19 @@ int rg_host_free(void* ptr);
 /* NumPy-compatible float32 linspace (host arithmetic; testable without a GPU) */
 int rg_linspace_f32(double start, double stop, int32_t num, float* out);
 
+/* ---- gate coordinates ----------------------------------------------------------------------------- */
+/* Cartesian gate coordinates from the scan's polar description, on the device, so that a table build ships
+ * (n_gates_per_ray + 2 n_rays) * 4 bytes instead of 12 bytes per gate.  Replaces the arrays the reference reads through
+ * get_gate_coordinates (reference utils.py:12-38: radar.gate_x / gate_y / gate_z, which pyart derives with its 4/3-earth
+ * antenna_to_cartesian): in float64
+ *     z = sqrt(r^2 + R^2 + 2 r R sin(el)) - R,  s = R asin(r cos(el) / (R + z)),  x = s sin(az),  y = s cos(az),
+ *     R = 4/3 * 6 371 000 m,
+ * rounded once to float32; gate id = ray * n_bins + bin.  range_m[n_bins] in metres, azimuth_deg / elevation_deg[n_rays]
+ * in degrees (float32, host or device per `memspace_in`); x, y, z [n_rays * n_bins] float32 in `memspace_out`. */
+int rg_gate_coordinates(rg_context* ctx, const float* range_m, const float* azimuth_deg, const float* elevation_deg,
+                        int64_t n_rays, int64_t n_bins, int32_t memspace_in, float* x, float* y, float* z,
+                        int32_t memspace_out);
+
 /* ---- neighbour table (K1-K3) ---------------------------------------------------------------------- */
 /* Replaces compute_grid_geometry / _process_single_level (reference compute.py:106-284, 18-103):
  * TOA cull `gate_z - radar_altitude <= toa` (float32), counting-sort binning into a uniform cell grid,

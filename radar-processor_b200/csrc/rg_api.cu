@@ -376,6 +376,26 @@ __global__ void __launch_bounds__(256) plane_filter_kernel(const T* __restrict__
     out[i] = hit ? fill : v;
 }
 
+// pyart's antenna_to_cartesian (4/3 effective earth radius), float64 with one rounding per operation, then float32
+__global__ void __launch_bounds__(256) gate_xyz_kernel(const float* __restrict__ range_m, const float* __restrict__ az_deg,
+                                                       const float* __restrict__ el_deg, int64_t n_rays, int64_t n_bins,
+                                                       float* __restrict__ x, float* __restrict__ y, float* __restrict__ z)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_rays * n_bins) return;
+    const int64_t ray = g / n_bins, bin = g - ray * n_bins;
+    const double R = 4.0 / 3.0 * 6371000.0;
+    const double deg = 3.14159265358979323846 / 180.0;              // np.radians: x * (pi / 180)
+    const double r = (double)__ldg(range_m + bin);
+    const double el = __dmul_rn((double)__ldg(el_deg + ray), deg), az = __dmul_rn((double)__ldg(az_deg + ray), deg);
+    const double zz = __dsub_rn(__dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(r, r), __dmul_rn(R, R)),
+                                                     __dmul_rn(__dmul_rn(__dmul_rn(2.0, r), R), sin(el)))), R);
+    const double s = __dmul_rn(R, asin(__ddiv_rn(__dmul_rn(r, cos(el)), __dadd_rn(R, zz))));
+    x[g] = (float)__dmul_rn(s, sin(az));
+    y[g] = (float)__dmul_rn(s, cos(az));
+    z[g] = (float)zz;
+}
+
 inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 }  // namespace
@@ -534,6 +554,48 @@ int rg_linspace_f32(double start, double stop, int32_t num, float* out)
 {
     if (num < 0 || (num > 0 && !out)) return fail(RG_ERR_INVALID, "bad argument");
     linspace_f32(start, stop, num, out);
+    return RG_OK;
+}
+
+// ---- gate coordinates ---------------------------------------------------------------------------------
+int rg_gate_coordinates(rg_context* c, const float* range_m, const float* azimuth_deg, const float* elevation_deg,
+                        int64_t n_rays, int64_t n_bins, int32_t memspace_in, float* x, float* y, float* z, int32_t memspace_out)
+{
+    Context* ctx = reinterpret_cast<Context*>(c);
+    RG_ENTER(ctx);
+    if (n_rays < 0 || n_bins < 0 || n_rays * n_bins >= 0xFFFFFFFFll) return fail(RG_ERR_INVALID, "n_rays * n_bins out of range");
+    if ((memspace_in != RG_DEVICE && memspace_in != RG_HOST) || (memspace_out != RG_DEVICE && memspace_out != RG_HOST))
+        return fail(RG_ERR_INVALID, "bad memspace");
+    const int64_t n = n_rays * n_bins;
+    if (n == 0) return RG_OK;
+    if (!range_m || !azimuth_deg || !elevation_deg || !x || !y || !z) return fail(RG_ERR_INVALID, "NULL pointer");
+    const float *dr = range_m, *da = azimuth_deg, *de = elevation_deg;
+    if (memspace_in == RG_HOST) {
+        RG_TRY(ensure(ctx, ctx->stage_in, align256((size_t)n_bins * 4) + 2 * align256((size_t)n_rays * 4)));
+        char* cur = (char*)ctx->stage_in.ptr;
+        RG_CUDA(cudaMemcpyAsync(cur, range_m, (size_t)n_bins * 4, cudaMemcpyHostToDevice, ctx->stream));
+        dr = (const float*)cur; cur += align256((size_t)n_bins * 4);
+        RG_CUDA(cudaMemcpyAsync(cur, azimuth_deg, (size_t)n_rays * 4, cudaMemcpyHostToDevice, ctx->stream));
+        da = (const float*)cur; cur += align256((size_t)n_rays * 4);
+        RG_CUDA(cudaMemcpyAsync(cur, elevation_deg, (size_t)n_rays * 4, cudaMemcpyHostToDevice, ctx->stream));
+        de = (const float*)cur;
+    }
+    float *dx = x, *dy = y, *dz = z;
+    if (memspace_out == RG_HOST) {
+        RG_TRY(ensure(ctx, ctx->stage_out, 3 * align256((size_t)n * 4)));
+        dx = (float*)ctx->stage_out.ptr;
+        dy = (float*)((char*)dx + align256((size_t)n * 4));
+        dz = (float*)((char*)dy + align256((size_t)n * 4));
+    }
+    gate_xyz_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dr, da, de, n_rays, n_bins, dx, dy, dz);
+    ctx->launches++;
+    RG_CUDA(cudaGetLastError());
+    if (memspace_out == RG_HOST) {
+        RG_CUDA(cudaMemcpyAsync(x, dx, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        RG_CUDA(cudaMemcpyAsync(y, dy, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        RG_CUDA(cudaMemcpyAsync(z, dz, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (memspace_in == RG_HOST || memspace_out == RG_HOST) RG_CUDA(cudaStreamSynchronize(ctx->stream));
     return RG_OK;
 }
 

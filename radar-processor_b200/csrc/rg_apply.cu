@@ -49,7 +49,10 @@ namespace rg {
 #endif
 
 #ifndef RG_MASKBITS
-#define RG_MASKBITS 1          // 1: odd field counts keep a mask-bit word in the free record slot (see Layout); 0: marker values only
+#define RG_MASKBITS 0          // 1: odd field counts keep a mask-bit word in the free record slot (see Layout): packed FFMA2 value sums
+                               //    and R2P predicates, 14 % fewer instructions -- and 16 % SLOWER (0.768 vs 0.663 ms): the kernel is
+                               //    bound by the bytes its gathers pull through L1 (8 instead of 4 for array B) and by load latency,
+                               //    not by issue slots (profiles/r02_maskbits_vs_marker.md).  0 (default): marker values only.
 #endif
 
 // ------------------------------------------------------------------------------------------------------
@@ -67,38 +70,27 @@ template <int F>
 struct Layout {
     static constexpr int FP = F == 1 ? 1 : F == 2 ? 2 : F <= 4 ? 4 : 8;
     static constexpr int FA = F == 1 ? 1 : F == 2 ? 2 : 4;
-    static constexpr int FB = F <= 4 ? 0 : F <= 6 ? 2 : 4;
+    static constexpr int FB = F <= 4 ? 0 : F == 5 ? (RG_MASKBITS ? 2 : 1) : F == 6 ? 2 : 4;
     static constexpr int NV = FA + FB;           // floats gathered per gate
     static constexpr bool MB = RG_MASKBITS && (F == 3 || F == 5 || F == 7);   // mask bits in slot F = NV - 1
     static constexpr int SH = F <= 5 ? 1 : 0;    // R2P fills P1.. in one instruction; bit 0 would cost two more
 };
 
+// One gate: field mask | masked_invalid | fused range rules -> the gate's record values (see Layout).
 template <int F>
-__global__ void __launch_bounds__(256) pack_records_kernel(const __grid_constant__ PackParams p)
+__device__ __forceinline__ void pack_gate(const PackParams& p, bool null_gate, uint32_t excluded, const float (&val)[F],
+                                          const uint32_t (&msk)[F], float (&out)[Layout<F>::NV])
 {
     using L = Layout<F>;
-    constexpr int FA = L::FA, FB = L::FB, NV = L::NV;
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g > p.n_gates) return;
-    const bool null_gate = g == p.n_gates;       // record n_gates is all-masked: a harmless target for idle lanes
-
-    // one exclusion bit per field from the fused range rules (filters.py:133-134, 156-157, 208-209)
-    uint32_t excluded = 0;
-    for (int r = 0; r < p.n_rules && !null_gate; ++r) {
-        const float q = __ldg(p.rule_values[r] + g);
-        const bool hit = (p.rule_use_lo[r] && q < p.rule_lo[r]) || (p.rule_use_hi[r] && q > p.rule_hi[r]);
-        if (hit) excluded |= p.rule_bits[r];
-    }
-
-    float out[NV];
     uint32_t mask_bits = 0;
 #pragma unroll
-    for (int f = 0; f < (L::MB ? F : NV); ++f) {
+    for (int f = 0; f < L::NV; ++f) out[f] = __uint_as_float(kMaskedBits);
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
         uint32_t bits = kMaskedBits;
-        if (f < F && !null_gate) {
-            const float v = __ldg(p.fields[f] + g);
-            bool masked = (excluded >> f) & 1u;
-            if (p.masks[f] != nullptr) masked |= __ldg(p.masks[f] + g) != 0;
+        if (!null_gate) {
+            const float v = val[f];
+            bool masked = ((excluded >> f) & 1u) || msk[f] != 0;
             if ((p.invalid_bits >> f) & 1u) masked |= !isfinite(v);          // np.ma.masked_invalid
             bits = masked ? kMaskedBits : (isnan(v) ? kCanonNaN : __float_as_uint(v));
         }
@@ -111,6 +103,35 @@ __global__ void __launch_bounds__(256) pack_records_kernel(const __grid_constant
         }
     }
     if constexpr (L::MB) out[F] = __uint_as_float(mask_bits);
+}
+
+__device__ __forceinline__ uint32_t rule_hits(const PackParams& p, int r, float q)
+{
+    // one exclusion bit per field from the fused range rules (filters.py:133-134, 156-157, 208-209)
+    const bool hit = (p.rule_use_lo[r] && q < p.rule_lo[r]) || (p.rule_use_hi[r] && q > p.rule_hi[r]);
+    return hit ? p.rule_bits[r] : 0u;
+}
+
+// Scalar form: one thread per gate, any pointer alignment.  Also writes the all-masked record n_gates.
+template <int F>
+__global__ void __launch_bounds__(256) pack_records_kernel(const __grid_constant__ PackParams p, int64_t first)
+{
+    using L = Layout<F>;
+    constexpr int FA = L::FA, FB = L::FB, NV = L::NV;
+    const int64_t g = first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > p.n_gates) return;
+    const bool null_gate = g == p.n_gates;       // record n_gates is all-masked: a harmless target for idle lanes
+    uint32_t excluded = 0;
+    for (int r = 0; r < p.n_rules && !null_gate; ++r) excluded |= rule_hits(p, r, __ldg(p.rule_values[r] + g));
+    float val[F];
+    uint32_t msk[F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+        val[f] = null_gate ? 0.f : __ldg(p.fields[f] + g);
+        msk[f] = (!null_gate && p.masks[f] != nullptr) ? __ldg(p.masks[f] + g) : 0u;
+    }
+    float out[NV];
+    pack_gate<F>(p, null_gate, excluded, val, msk, out);
     auto store = [](float* dst, const float* v, auto n) {
         constexpr int N = decltype(n)::value;
         if constexpr (N == 1) dst[0] = v[0];
@@ -121,6 +142,53 @@ __global__ void __launch_bounds__(256) pack_records_kernel(const __grid_constant
     if constexpr (FB > 0) store(p.records_b + (size_t)g * FB, out + FA, std::integral_constant<int, FB>{});
 }
 
+// Vector form: four consecutive gates per thread -- 128-bit loads of every field (32-bit of every mask), and the four
+// records leave as whole 128-bit stores (array B of a five-field pass: ONE store for the four gates).  HBM-bound
+// streaming: 4 F G bytes in, 4 (FA + FB) G out.  Needs 16-byte aligned field / rule pointers and 4-byte aligned masks
+// (launch_pack checks and otherwise takes the scalar kernel); the last G mod 4 gates and the all-masked record are
+// written by a scalar launch.
+template <int F>
+__global__ void __launch_bounds__(256) pack_records4_kernel(const __grid_constant__ PackParams p, int64_t n_quads)
+{
+    using L = Layout<F>;
+    constexpr int FA = L::FA, FB = L::FB, NV = L::NV;
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_quads) return;
+    uint32_t excluded[4] = {0u, 0u, 0u, 0u};
+    for (int r = 0; r < p.n_rules; ++r) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p.rule_values[r]) + q);
+        excluded[0] |= rule_hits(p, r, t.x); excluded[1] |= rule_hits(p, r, t.y);
+        excluded[2] |= rule_hits(p, r, t.z); excluded[3] |= rule_hits(p, r, t.w);
+    }
+    float val[4][F];
+    uint32_t msk[4][F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p.fields[f]) + q);
+        val[0][f] = t.x; val[1][f] = t.y; val[2][f] = t.z; val[3][f] = t.w;
+        const uint32_t m = p.masks[f] != nullptr ? __ldg(reinterpret_cast<const uint32_t*>(p.masks[f]) + q) : 0u;
+        msk[0][f] = m & 0xFFu; msk[1][f] = (m >> 8) & 0xFFu; msk[2][f] = (m >> 16) & 0xFFu; msk[3][f] = m >> 24;
+    }
+    float a[4 * FA], b[FB > 0 ? 4 * FB : 1];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float out[NV];
+        pack_gate<F>(p, false, excluded[k], val[k], msk[k], out);
+#pragma unroll
+        for (int i = 0; i < FA; ++i) a[k * FA + i] = out[i];
+#pragma unroll
+        for (int i = 0; i < FB; ++i) b[k * FB + i] = out[FA + i];
+    }
+    float4* da = reinterpret_cast<float4*>(p.records + (size_t)q * 4 * FA);
+#pragma unroll
+    for (int i = 0; i < FA; ++i) da[i] = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+    if constexpr (FB > 0) {
+        float4* db = reinterpret_cast<float4*>(p.records_b + (size_t)q * 4 * FB);
+#pragma unroll
+        for (int i = 0; i < FB; ++i) db[i] = make_float4(b[4 * i], b[4 * i + 1], b[4 * i + 2], b[4 * i + 3]);
+    }
+}
+
 // (Re)create the texture objects over the record arrays when the buffer or the field count changed.
 int bind_record_textures(Context* ctx, const float* rec_a, const float* rec_b, int n_fields, int64_t n_gates)
 {
@@ -129,7 +197,7 @@ int bind_record_textures(Context* ctx, const float* rec_a, const float* rec_b, i
     if (ctx->tex_a) { cudaDestroyTextureObject(ctx->tex_a); ctx->tex_a = 0; }
     if (ctx->tex_b) { cudaDestroyTextureObject(ctx->tex_b); ctx->tex_b = 0; }
     const int fa = n_fields == 1 ? 1 : n_fields == 2 ? 2 : 4;
-    const int fb = n_fields <= 4 ? 0 : n_fields <= 6 ? 2 : 4;
+    const int fb = n_fields <= 4 ? 0 : n_fields == 5 ? (RG_MASKBITS ? 2 : 1) : n_fields == 6 ? 2 : 4;
     auto make = [&](const float* ptr, int nf, unsigned long long* out) -> int {
         cudaResourceDesc rd{};
         rd.resType = cudaResourceTypeLinear;
@@ -160,22 +228,43 @@ size_t records_b_offset(int n_fields, int64_t n_gates)
     return (((size_t)(n_gates + 1) * fa * sizeof(float)) + 511) & ~(size_t)511;   // texture-bindable
 }
 
+#ifndef RG_PACK4
+#define RG_PACK4 1             // vector pack kernel (four gates per thread) when the pointers allow it
+#endif
+
+template <int F>
+static void launch_pack_f(Context* ctx, const PackParams& p, bool vec)
+{
+    int64_t first = 0;
+    if (vec && p.n_gates >= 4) {
+        const int64_t n_quads = p.n_gates / 4;
+        pack_records4_kernel<F><<<(unsigned)((n_quads + 255) / 256), 256, 0, ctx->stream>>>(p, n_quads);
+        ctx->launches++;
+        first = n_quads * 4;
+    }
+    const int64_t rest = p.n_gates + 1 - first;              // the tail and the all-masked record n_gates
+    pack_records_kernel<F><<<(unsigned)((rest + 255) / 256), 256, 0, ctx->stream>>>(p, first);
+    ctx->launches++;
+}
+
 int launch_pack(Context* ctx, const PackParams& p)
 {
-    const unsigned blocks = (unsigned)((p.n_gates + 1 + 255) / 256);
+    bool vec = RG_PACK4 != 0;
+    for (int f = 0; f < p.n_fields; ++f)
+        vec = vec && ((uintptr_t)p.fields[f] % 16 == 0) && (p.masks[f] == nullptr || (uintptr_t)p.masks[f] % 4 == 0);
+    for (int r = 0; r < p.n_rules; ++r) vec = vec && ((uintptr_t)p.rule_values[r] % 16 == 0);
     timer_begin(ctx, kTimerPack);
     switch (p.n_fields) {
-        case 1: pack_records_kernel<1><<<blocks, 256, 0, ctx->stream>>>(p); break;
-        case 2: pack_records_kernel<2><<<blocks, 256, 0, ctx->stream>>>(p); break;
-        case 3: pack_records_kernel<3><<<blocks, 256, 0, ctx->stream>>>(p); break;
-        case 4: pack_records_kernel<4><<<blocks, 256, 0, ctx->stream>>>(p); break;
-        case 5: pack_records_kernel<5><<<blocks, 256, 0, ctx->stream>>>(p); break;
-        case 6: pack_records_kernel<6><<<blocks, 256, 0, ctx->stream>>>(p); break;
-        case 7: pack_records_kernel<7><<<blocks, 256, 0, ctx->stream>>>(p); break;
-        default: pack_records_kernel<8><<<blocks, 256, 0, ctx->stream>>>(p); break;
+        case 1: launch_pack_f<1>(ctx, p, vec); break;
+        case 2: launch_pack_f<2>(ctx, p, vec); break;
+        case 3: launch_pack_f<3>(ctx, p, vec); break;
+        case 4: launch_pack_f<4>(ctx, p, vec); break;
+        case 5: launch_pack_f<5>(ctx, p, vec); break;
+        case 6: launch_pack_f<6>(ctx, p, vec); break;
+        case 7: launch_pack_f<7>(ctx, p, vec); break;
+        default: launch_pack_f<8>(ctx, p, vec); break;
     }
     timer_end(ctx, kTimerPack);
-    ctx->launches++;
     RG_CUDA(cudaGetLastError());
     return RG_OK;
 }
@@ -1411,7 +1500,7 @@ __global__ void __launch_bounds__(128) apply_reference_order_kernel(const __grid
         if (e > s) {
             const int nf = p.n_fields;                             // see Layout<F>
             const int fa = nf == 1 ? 1 : nf == 2 ? 2 : 4;
-            const int fb = nf <= 4 ? 0 : nf <= 6 ? 2 : 4;
+            const int fb = nf <= 4 ? 0 : nf == 5 ? (RG_MASKBITS ? 2 : 1) : nf == 6 ? 2 : 4;
             const bool mb = RG_MASKBITS && (nf == 3 || nf == 5 || nf == 7);   // mask word in slot nf: A[3], B[1] or B[3]
             RowTerms<FP> t{p.pairs, f < fa ? p.records : p.records_b, f, false, f < fa ? fa : fb, f < fa ? f : f - fa,
                            mb ? (nf == 3 ? p.records : p.records_b) : nullptr, nf == 3 ? fa : fb, mb ? (nf == 3 ? 3 : nf - fa) : -1,

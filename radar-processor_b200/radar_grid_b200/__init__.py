@@ -14,7 +14,8 @@ from ._native import get_device, pinned_empty, set_device
 from .geometry import GridGeometry, load_geometry, save_geometry
 from .compute import compute_grid_geometry
 from .interpolate import apply_geometry, apply_geometry_multi
-from .utils import get_available_fields, get_field_data, get_gate_coordinates, get_radar_altitude, get_radar_info
+from .utils import (get_available_fields, get_field_data, get_gate_coordinates, get_gate_coordinates_device, get_radar_altitude,
+                    get_radar_info)
 from .filters import GateFilter, GridFilter, create_mask_from_filter
 from .products import (EARTH_RADIUS, EFFECTIVE_RADIUS_FACTOR, column_max, column_mean, column_min,
                        compute_beam_height, compute_beam_height_flat, compute_beam_height_simple,
@@ -29,7 +30,7 @@ __version__ = "0.1.0"
 __all__ = [
     "GridGeometry", "save_geometry", "load_geometry", "compute_grid_geometry",
     "apply_geometry", "apply_geometry_multi",
-    "get_gate_coordinates", "get_field_data", "get_available_fields", "get_radar_info", "get_radar_altitude",
+    "get_gate_coordinates", "get_gate_coordinates_device", "get_field_data", "get_available_fields", "get_radar_info", "get_radar_altitude",
     "GateFilter", "GridFilter", "create_mask_from_filter",
     "constant_altitude_ppi", "constant_elevation_ppi", "column_max", "column_min", "column_mean",
     "get_elevation_from_z_level", "get_beam_height_difference", "compute_beam_height",

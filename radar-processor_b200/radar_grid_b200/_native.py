@@ -98,6 +98,8 @@ _PROTOTYPES = {
     "rg_geometry_export_csr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                          C.c_int32]),
     "rg_geometry_destroy": (C.c_int, [C.c_void_p]),
+    "rg_gate_coordinates": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "rg_geometry_level_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                           C.POINTER(GridSpec), C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32,
                                           C.POINTER(C.c_int64)]),

@@ -15,6 +15,37 @@ def get_gate_coordinates(radar) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     return tuple(getattr(radar, k)["data"].ravel().astype("float32") for k in ("gate_x", "gate_y", "gate_z"))
 
 
+def get_gate_coordinates_device(radar, ctx=None):
+    """
+    The same three arrays as torch CUDA tensors, computed ON the device from the scan's polar description
+    (radar.range, radar.azimuth, radar.elevation: a few kilobytes) instead of being read from radar.gate_x / gate_y /
+    gate_z and shipped (12 bytes per gate): pyart's 4/3-earth antenna_to_cartesian in float64, rounded to float32
+    (``rg_gate_coordinates``).  Feed them to ``DeviceGeometry.build``; radar.gate_x & co. are never touched, so pyart's
+    lazy evaluation of them never runs.
+    """
+    import ctypes as C
+    import torch
+    from . import _native as N
+    ctx = ctx or N.default_context()
+    rng = np.ascontiguousarray(radar.range["data"], dtype=np.float32)
+    az = np.ascontiguousarray(radar.azimuth["data"], dtype=np.float32)
+    el = np.ascontiguousarray(radar.elevation["data"], dtype=np.float32)
+    if az.shape != el.shape:
+        raise ValueError("azimuth and elevation must have one entry per ray")
+    n = az.shape[0] * rng.shape[0]
+    dev = torch.device("cuda", ctx.device)
+    with torch.cuda.device(dev):
+        polar = torch.from_numpy(np.concatenate([rng, az, el])).to(dev)
+        out = torch.empty((3, n), dtype=torch.float32, device=dev)
+    nb, nr = rng.shape[0], az.shape[0]
+    base = polar.data_ptr()
+    with N.torch_stream_order(ctx, True):
+        N.check(N.lib().rg_gate_coordinates(ctx.handle, base, base + 4 * nb, base + 4 * (nb + nr), nr, nb, N.RG_DEVICE,
+                                            out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), N.RG_DEVICE))
+    del polar
+    return out[0], out[1], out[2]
+
+
 def get_field_data(radar, field_name: str) -> np.ndarray:
     """Flattened float32 masked array of one field; NaN/Inf and pre-existing masks are masked."""
     return np.ma.masked_invalid(radar.fields[field_name]["data"]).ravel().astype("float32")

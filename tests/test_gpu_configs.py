@@ -267,3 +267,33 @@ def test_compute_grid_geometry_builds_a_table_once(tmp_path):
     assert c.device_geometry() is not a.device_geometry()
     np.testing.assert_array_equal(a.indptr, b.indptr)
     cache.clear()
+
+
+def test_gate_coordinates_on_the_device_match_the_float64_transform():
+    """rg_gate_coordinates: pyart's 4/3-earth antenna_to_cartesian from (range, azimuth, elevation) on the device, in
+    float64, rounded once to float32 -- against the same formula in NumPy on the same float32 inputs (CUDA and libm
+    sin / cos / asin differ by <= 1 ulp in float64, so a float32 result may land on the neighbouring value: a handful
+    per million at most), and the table built from the device coordinates against the one built from the host ones."""
+    import torch
+    spec = S.SPECS["cfg1"]
+    radar = S.SyntheticRadar(spec, seed=0)
+    gx, gy, gz = rg.get_gate_coordinates_device(radar)
+    assert gx.is_cuda and gx.dtype == torch.float32 and gx.numel() == spec.n_gates
+    R = 4.0 / 3.0 * 6371000.0
+    rng = radar.range["data"].astype(np.float64)[None, :]
+    el = np.radians(radar.elevation["data"].astype(np.float64))[:, None]
+    az = np.radians(radar.azimuth["data"].astype(np.float64))[:, None]
+    z = np.sqrt(rng * rng + R * R + 2.0 * rng * R * np.sin(el)) - R
+    s = R * np.arcsin(rng * np.cos(el) / (R + z))
+    want = [(s * np.sin(az)).ravel().astype(np.float32), (s * np.cos(az)).ravel().astype(np.float32), z.ravel().astype(np.float32)]
+    for got, w, name in zip((gx, gy, gz), want, "xyz"):
+        g = got.cpu().numpy()
+        ulp = np.abs(g.view(np.int32).astype(np.int64) - w.view(np.int32).astype(np.int64))
+        near_zero = np.abs(w) < 1e-3                       # sin(180 deg) * s: absolute, not relative, agreement there
+        assert ulp[~near_zero].max() <= 1 and (ulp[~near_zero] > 0).mean() < 1e-4, (name, int(ulp[~near_zero].max()))
+        assert np.abs(g[near_zero] - w[near_zero]).max(initial=0.0) < 1e-6
+    kw = dict(min_radius=spec.min_radius, beam_factor=spec.beam_factor, weighting=spec.weighting, toa=spec.toa)
+    dev_d = rg.DeviceGeometry.build(gx, gy, gz, spec.grid_shape, spec.grid_limits, **kw)
+    dev_h = rg.DeviceGeometry.build(gx.cpu().numpy(), gy.cpu().numpy(), gz.cpu().numpy(), spec.grid_shape, spec.grid_limits, **kw)
+    for a, b in zip(dev_d.export_csr(), dev_h.export_csr()):
+        np.testing.assert_array_equal(a, b)

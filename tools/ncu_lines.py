@@ -2,7 +2,7 @@
 """Per-source-line view of an ncu capture: joins `ncu --page source --csv` (per SASS instruction: executed count,
 stall samples) with the line table of the same kernel from `nvdisasm -g`.
 
-    python tools/ncu_lines.py <rep.ncu-rep> <lib.so> <mangled kernel name> [top N]
+    python tools/ncu_lines.py <rep.ncu-rep | source-page.csv> <lib.so> <mangled kernel name> [top N]
 """
 import collections
 import csv
@@ -45,7 +45,8 @@ def main():
     rep, lib, kernel = sys.argv[1:4]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
     table = line_table(lib, kernel)
-    rows = list(csv.reader(io.StringIO(sh(["ncu", "-i", rep, "--page", "source", "--csv"]).stdout)))
+    text = open(rep).read() if rep.endswith(".csv") else sh(["ncu", "-i", rep, "--page", "source", "--csv"]).stdout
+    rows = list(csv.reader(io.StringIO(text)))
     hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
     hdr = rows[hdr_i]
     ia, isrc, iex, ismp = hdr.index("Address"), hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples")

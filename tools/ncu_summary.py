@@ -2,6 +2,8 @@
 """Summarise an .ncu-rep (one `ncu --set full` capture) into the handful of numbers the roofline discussion uses.
 
     python tools/ncu_summary.py gpurun_out/prof_apply.ncu-rep [launch_index] > profiles/<name>.md
+    python tools/ncu_summary.py gpurun_out/<name>            # reads <name>.raw.csv + <name>.source.csv (tools/gpu_ncu_apply.sh)
+    python tools/ncu_summary.py gpurun_out/<name> --traffic cfg3   # also rewrites profiles/apply_traffic.json, stamped with the kernel sources' hash
 """
 import collections
 import csv
@@ -11,6 +13,7 @@ import subprocess
 import sys
 
 KEYS = [
+    "l1tex__t_requests_pipe_lsu_mem_local_op_st.sum",
     "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
     "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
     "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
@@ -31,8 +34,10 @@ def run(args):
 
 def main():
     rep = sys.argv[1]
-    which = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-    rows = list(csv.reader(io.StringIO(run(["-i", rep, "--page", "raw", "--csv"]))))
+    which = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 0
+    from_csv = not rep.endswith(".ncu-rep")
+    raw_text = open(rep + ".raw.csv").read() if from_csv else run(["-i", rep, "--page", "raw", "--csv"])
+    rows = list(csv.reader(io.StringIO(raw_text)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     r = data[which]
     name = r[hdr.index("Kernel Name")]
@@ -43,7 +48,20 @@ def main():
             i = hdr.index(k)
             print(f"| {k} | {r[i]} | {units[i]} |")
     # instruction mix + stall reasons from the SASS page
-    sass = list(csv.reader(io.StringIO(run(["-i", rep, "--page", "source", "--csv", "--print-source", "sass"]))))
+    if "--traffic" in sys.argv:
+        import hashlib, json, os
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        hh = hashlib.sha256()
+        for f in ("rg_apply.cu", "rg_geometry.cu", "rg_api.cu", "rg_internal.cuh"):
+            hh.update(open(os.path.join(root, "radar-processor_b200", "csrc", f), "rb").read())
+        to_bytes = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        tot = sum(float(r[hdr.index(k)]) * to_bytes[units[hdr.index(k)]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        doc = {"workload": sys.argv[sys.argv.index("--traffic") + 1], "kernel": name, "traffic_bytes_per_launch": tot,
+               "source": os.path.basename(rep), "source_sha256": hh.hexdigest(),
+               "how": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of the apply kernel"}
+        json.dump(doc, open(os.path.join(root, "profiles", "apply_traffic.json"), "w"), indent=1)
+    sass_text = open(rep + ".source.csv").read() if from_csv else run(["-i", rep, "--page", "source", "--csv", "--print-source", "sass"])
+    sass = list(csv.reader(io.StringIO(sass_text)))
     hi = [i for i, x in enumerate(sass) if x and x[0] == "Address"]
     if hi:
         h = sass[hi[0]]
