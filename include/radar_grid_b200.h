@@ -47,7 +47,11 @@ typedef enum rg_status {
 typedef enum rg_memspace { RG_HOST = 0, RG_DEVICE = 1 } rg_memspace;
 
 /* reference compute.py:82-87 */
-typedef enum rg_weighting { RG_W_BARNES2 = 0, RG_W_CRESSMAN = 1, RG_W_NEAREST = 2 } rg_weighting;
+/* BARNES2 / CRESSMAN / NEAREST are the reference's weighting functions (compute.py:82-87; 'nearest' = weight 1 for EVERY
+ * gate in the ROI).  DIST2 stores float32(d^2) in the weight slot: the table of the nearest-GATE gridding that
+ * process_radar_to_cog asks pyart for (weighting_function='nearest', processor.py:152-163), applied with
+ * rg_apply_args.reference_order = 2. */
+typedef enum rg_weighting { RG_W_BARNES2 = 0, RG_W_CRESSMAN = 1, RG_W_NEAREST = 2, RG_W_DIST2 = 3 } rg_weighting;
 
 /* Target grid.  Axes are float32 linspace(lo, hi, n) inclusive, computed with NumPy's formula
  * (reference compute.py:184-186).  [z_begin, z_end) selects the z-slab a geometry / grid covers; the
@@ -194,7 +198,9 @@ typedef struct rg_image {
  * then only the RGBA image is written).  z indices are GLOBAL level indices (0..nz-1), inclusive. */
 typedef struct rg_product {
     int32_t kind;              /* rg_product_kind */
-    int32_t mode;              /* rg_blend_mode (LEVEL); for BEAM: 0 = 'linear', 1 = 'nearest' */
+    int32_t mode;              /* rg_blend_mode (LEVEL); for BEAM: 0 = 'linear', 1 = 'nearest', 2 = radar_processor's own collapse
+                                * (processor.py:513-528): level closest to r sin(el) + r^2 / (2 * 8.49e6) on float64 axes, no
+                                * out-of-grid NaN; uses sin_elev only */
     int32_t z_lo, z_hi;
     int32_t earth_curvature;   /* BEAM */
     int32_t partial;           /* 0: the finished product.  1: this z-slab's TERM of it, to be combined across slabs by one
@@ -222,7 +228,8 @@ typedef enum rg_plane_filter_kind {
     RG_PF_BELOW = 1,           /* apply_below:   in <  a            */
     RG_PF_ABOVE = 2,           /* apply_above:   in >  a            */
     RG_PF_OUTSIDE = 3,         /* apply_outside_range: in < a || in > b */
-    RG_PF_INVALID = 4          /* apply_invalid: NaN or Inf          */
+    RG_PF_INVALID = 4,         /* apply_invalid: NaN or Inf          */
+    RG_PF_BELOW_EQUAL = 5      /* in <= a: np.ma.masked_less_equal(arr, vmin), radar_processor's re-mask (processor.py:541-546) */
 } rg_plane_filter_kind;
 int rg_plane_filter(rg_context* ctx, const void* in, void* out, int64_t n, int32_t elem_bits, int32_t kind,
                     double a, double b, double fill_value, int32_t memspace);
@@ -243,7 +250,10 @@ typedef struct rg_apply_args {
     int32_t n_fields;                      /* 1..RG_MAX_FIELDS */
     int32_t n_rules;                       /* 0..RG_MAX_RULES */
     int32_t n_products;                    /* COLMAX/COLMIN/COLMEAN at most one each, <= RG_MAX_SLICES slices */
-    int32_t reference_order;               /* 1: np.add.reduceat summation order -> bit-exact vs reference */
+    int32_t reference_order;               /* 0: fast fused path.  1: np.add.reduceat summation order -> bit-exact vs reference.
+                                            * 2: nearest-gate gridding on a RG_W_DIST2 table: every voxel takes, per field, the
+                                            *    value of the closest gate whose value is not masked (ties: lowest gate id);
+                                            *    Py-ART map_gates_to_grid, weighting_function='nearest' */
     uint32_t mask_invalid_bits;            /* bit f: NaN/Inf of field f are masked (np.ma.masked_invalid) */
     float fill_value;
     const float* const* fields;            /* [n_fields] -> float32[n_gates] */

@@ -389,3 +389,92 @@ def apply_colormap(data, lut, vmin=None, vmax=None, fill_value=None):
     rgba = (lut.take(idx, axis=0, mode="clip") * 255).astype(np.uint8)
     rgba[nodata, 3] = 0
     return rgba
+
+
+# --------------------------------------------------------------------------------------------------
+# f1  process_radar_to_cog's interpolation stage      reference: src/radar_processor/processor.py:128-163, 480-551
+# --------------------------------------------------------------------------------------------------
+
+def map_gates_to_grid_nearest(gate_x, gate_y, gate_z, fields, grid_shape, grid_limits, roi, gate_excluded=None, toa=17000.0):
+    """
+    PARITY UNPINNED.  What the reference asks Py-ART for (processor.py:152-163: pyart.map.grid_from_radars(...,
+    gridding_algo='map_gates_to_grid', weighting_function='nearest', roi_func='constant', constant_roi=roi,
+    gatefilters=gf)), restated from the published algorithm of arm-pyart's GateToGridMapper (pyart/map/_gate_to_grid_map.pyx,
+    2.x): arm-pyart is not vendored under /root/reference nor installed, and the reference's tests mock it.
+
+      for every gate (in gate order) not excluded by the gate filter and with z <= toa:
+          for every grid point with dist2 = dx^2 + dy^2 + dz^2 < roi^2:
+              for every field whose value at the gate is not masked:
+                  if dist2 < min_dist2[point, field]:  min_dist2 = dist2; value[point, field] = gate value
+      points no gate reached are masked.
+
+    Distances here are float64 on the float32 gate coordinates and the float32 grid axes the rest of this package uses
+    (Py-ART evaluates them in float32 on float64 axes: near-ties may resolve differently — part of "unpinned").
+    Brute force over grid points: small cases only.  fields: {name: masked float32[n_gates]} -> {name: masked (nz, ny, nx)}.
+    """
+    z_ax, y_ax, x_ax = grid_axes(grid_shape, grid_limits)
+    gx, gy, gz = (np.asarray(a, dtype=np.float32).astype(np.float64) for a in (gate_x, gate_y, gate_z))
+    ok = gz.astype(np.float32) <= np.float32(toa)
+    if gate_excluded is not None:
+        ok &= ~np.asarray(gate_excluded, dtype=bool).ravel()
+    nz, ny, nx = grid_shape
+    out = {n: np.ma.masked_all((nz, ny, nx), dtype=np.float32) for n in fields}
+    data = {n: np.ma.getdata(f).astype(np.float32) for n, f in fields.items()}
+    valid = {n: ok & ~np.ma.getmaskarray(f).ravel() for n, f in fields.items()}
+    r2 = float(roi) * float(roi)
+    for iz in range(nz):
+        dz2 = (gz - float(z_ax[iz])) ** 2
+        near_z = dz2 < r2
+        for iy in range(ny):
+            dy2 = (gy - float(y_ax[iy])) ** 2
+            cand = np.nonzero(near_z & (dy2 < r2))[0]
+            if cand.size == 0:
+                continue
+            for ix in range(nx):
+                dx = gx[cand] - float(x_ax[ix])
+                d2 = (dx * dx + dy2[cand]) + dz2[cand]
+                inside = d2 < r2
+                if not inside.any():
+                    continue
+                idx, dd = cand[inside], d2[inside].astype(np.float32)     # the table stores float32(d2)
+                for n in fields:
+                    v = valid[n][idx]
+                    if v.any():
+                        k = np.argmin(np.where(v, dd, np.float32(np.inf)))   # first minimum = lowest gate id
+                        out[n][iz, iy, ix] = data[n][idx[k]]
+    return out
+
+
+def collapse_field_3d_to_2d(data3d, product, x_coords=None, y_coords=None, z_levels=None, elevation_deg=None,
+                            target_height_m=None):
+    """radar_processor/utils.py:336-387 (pure NumPy in the reference; the module cannot be imported because it imports
+    pyart at the top): 'ppi' level closest to r sin(el) + r^2 / (2 * 8.49e6), 'cappi' closest level, 'colmax' masked max."""
+    if data3d.ndim == 2:
+        arr2d = data3d
+    elif product == "ppi":
+        X, Y = np.meshgrid(x_coords, y_coords, indexing="xy")
+        r = np.sqrt(X ** 2 + Y ** 2)
+        Re = 8.49e6
+        z_target = r * np.sin(np.deg2rad(elevation_deg)) + (r ** 2) / (2.0 * Re)
+        iz = np.abs(z_target[..., None] - z_levels[None, None, :]).argmin(axis=2)
+        yy = np.arange(len(y_coords))[:, None]
+        xx = np.arange(len(x_coords))[None, :]
+        arr2d = data3d[iz, yy, xx]
+    elif product == "cappi":
+        iz = np.abs(z_levels - float(target_height_m)).argmin()
+        arr2d = data3d[iz, :, :]
+    elif product == "colmax":
+        arr2d = data3d.max(axis=0)
+    else:
+        raise ValueError("Producto inválido")
+    return np.ma.array(arr2d.astype(np.float32), mask=np.ma.getmaskarray(arr2d))
+
+
+def remask_2d(arr2d, field, vmin=-30.0):
+    """processor.py:541-546."""
+    arr2d = np.ma.masked_invalid(arr2d)
+    if field in ["filled_DBZH", "DBZH", "DBZV", "DBZHF", "composite_reflectivity"]:
+        arr2d = np.ma.masked_less_equal(arr2d, vmin)
+    elif field in ["KDP", "ZDR"]:
+        arr2d = np.ma.masked_less(arr2d, vmin)
+    return arr2d

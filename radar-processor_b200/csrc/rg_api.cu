@@ -182,7 +182,7 @@ int check_image(const rg_product& pr)
     if (pr.partial) return fail(RG_ERR_INVALID, "a partial (z-slab term) product has no image form");
     if (im.n_filters < 0 || im.n_filters > RG_MAX_IMAGE_FILTERS) return fail(RG_ERR_INVALID, "image: n_filters must be 0..4");
     for (int i = 0; i < im.n_filters; ++i)
-        if (im.filter_kind[i] < RG_PF_BELOW || im.filter_kind[i] > RG_PF_INVALID) return fail(RG_ERR_INVALID, "image: unknown filter kind");
+        if (im.filter_kind[i] < RG_PF_BELOW || im.filter_kind[i] > RG_PF_BELOW_EQUAL) return fail(RG_ERR_INVALID, "image: unknown filter kind");
     if (!isfinite(im.vmin) || !isfinite(im.vmax)) return fail(RG_ERR_INVALID, "image: vmin and vmax must be finite");
     if (im.vmin > im.vmax) return fail(RG_ERR_INVALID, "minvalue must be less than or equal to maxvalue");   // Normalize's ValueError
     if (im.lut_entries < 1 || im.lut_entries > 4096) return fail(RG_ERR_INVALID, "image: lut_entries must be 1..4096");
@@ -265,6 +265,8 @@ int make_product_params(const rg_grid_spec& gs, int n_products, const rg_product
     pp->z_step = gs.nz > 1 ? (gs.z_max - gs.z_min) / (double)(gs.nz - 1) : 1.0;
     pp->x_ax = x_ax;
     pp->y_ax = y_ax;
+    pp->nx = gs.nx; pp->ny = gs.ny;
+    pp->x_min = gs.x_min; pp->x_max = gs.x_max; pp->y_min = gs.y_min; pp->y_max = gs.y_max;
     int lo = gs.nz, hi = -1;
     if (n_products < 0) return fail(RG_ERR_INVALID, "n_products < 0");
     if (n_products > 0 && products == nullptr) return fail(RG_ERR_INVALID, "products is NULL");
@@ -312,7 +314,7 @@ int make_product_params(const rg_grid_spec& gs, int n_products, const rg_product
                     s.w_lo = pr.w_lo; s.w_hi = pr.w_hi;
                     lo = std::min(lo, std::min(s.z_lo, s.z_hi)); hi = std::max(hi, std::max(s.z_lo, s.z_hi));
                 } else {
-                    if (pr.mode != 0 && pr.mode != 1) return fail(RG_ERR_INVALID, "BEAM product: mode must be 0 (linear) or 1 (nearest)");
+                    if (pr.mode < 0 || pr.mode > 2) return fail(RG_ERR_INVALID, "BEAM product: mode must be 0 (linear), 1 (nearest) or 2 (closest level)");
                     s.curvature = pr.earth_curvature;
                     s.sin_e = pr.sin_elev; s.cos_c = pr.cos_elev_clamped; s.tan_e = pr.tan_elev;
                     s.ke_re = pr.ke_re; s.ke_re_sq = pr.ke_re_sq;
@@ -371,6 +373,7 @@ __global__ void __launch_bounds__(256) plane_filter_kernel(const T* __restrict__
         case RG_PF_BELOW: hit = v < a; break;                    // filters.py:660
         case RG_PF_ABOVE: hit = v > a; break;                    // filters.py:689
         case RG_PF_OUTSIDE: hit = (v < a) || (v > b); break;     // filters.py:721
+        case RG_PF_BELOW_EQUAL: hit = v <= a; break;             // processor.py:543 (masked_less_equal)
         default: hit = isnan(v) || isinf(v); break;              // filters.py:746
     }
     out[i] = hit ? fill : v;
@@ -611,7 +614,7 @@ int rg_geometry_build(rg_context* c, const float* gate_x, const float* gate_y, c
     RG_TRY(check_grid(grid));
     if (n_gates < 0 || n_gates >= 0xFFFFFFFFll) return fail(RG_ERR_INVALID, "n_gates out of range");
     if (n_gates > 0 && (!gate_x || !gate_y || !gate_z)) return fail(RG_ERR_INVALID, "gate coordinate pointer is NULL");
-    if (weighting != RG_W_BARNES2 && weighting != RG_W_CRESSMAN && weighting != RG_W_NEAREST)
+    if (weighting != RG_W_BARNES2 && weighting != RG_W_CRESSMAN && weighting != RG_W_NEAREST && weighting != RG_W_DIST2)
         return fail(RG_ERR_INVALID, "Unknown weighting function");
     if (!(min_radius >= 0.0) || !(beam_factor >= 0.0) || !isfinite(min_radius) || !isfinite(beam_factor))
         return fail(RG_ERR_INVALID, "min_radius and beam_factor must be finite and >= 0");
@@ -927,7 +930,7 @@ int rg_plane_filter(rg_context* c, const void* in, void* out, int64_t n, int32_t
     RG_ENTER(ctx);
     if (n < 0 || (n > 0 && (!in || !out))) return fail(RG_ERR_INVALID, "bad argument");
     if (elem_bits != 32 && elem_bits != 64) return fail(RG_ERR_INVALID, "elem_bits must be 32 or 64");
-    if (kind < RG_PF_BELOW || kind > RG_PF_INVALID) return fail(RG_ERR_INVALID, "unknown plane filter kind");
+    if (kind < RG_PF_BELOW || kind > RG_PF_BELOW_EQUAL) return fail(RG_ERR_INVALID, "unknown plane filter kind");
     if (memspace != RG_DEVICE && memspace != RG_HOST) return fail(RG_ERR_INVALID, "bad memspace");
     if (n == 0) return RG_OK;
     const size_t bytes = (size_t)n * (elem_bits / 8);
@@ -1035,7 +1038,9 @@ int rg_apply(rg_context* c, const rg_geometry* geom, const rg_apply_args* a, int
     RG_TRY(launch_pack(ctx, pk));
 
     // ---- outputs
-    const bool ref_order = a->reference_order != 0;
+    if (a->reference_order < 0 || a->reference_order > 2) return fail(RG_ERR_INVALID, "reference_order must be 0, 1 or 2");
+    const bool nearest_gate = a->reference_order == 2;
+    const bool ref_order = a->reference_order != 0;          // both exact modes are un-fused: grid, then stand-alone products
     const int n_products = a->n_products;
     bool want_grid[RG_MAX_FIELDS] = {};
     bool any_grid = false;
@@ -1108,7 +1113,7 @@ int rg_apply(rg_context* c, const rg_geometry* geom, const rg_apply_args* a, int
         ap.prod.any = 0;
         bool any = false;
         for (int f = 0; f < F; ++f) any |= ap.grid_out[f] != nullptr;
-        if (any) RG_TRY(launch_apply(ctx, g, ap, true));
+        if (any) RG_TRY(nearest_gate ? launch_apply_nearest(ctx, g, ap) : launch_apply(ctx, g, ap, true));
         if (n_products > 0) RG_TRY(launch_products(ctx, g->grid, F, grid_dev, pp));
     } else {
         // walk only the levels somebody needs

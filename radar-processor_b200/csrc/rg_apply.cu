@@ -229,7 +229,8 @@ size_t records_b_offset(int n_fields, int64_t n_gates)
 }
 
 #ifndef RG_PACK4
-#define RG_PACK4 1             // vector pack kernel (four gates per thread) when the pointers allow it
+#define RG_PACK4 0             // 1: vector pack kernel (four gates per thread) when the pointers allow it; measured 46 vs 42 us for the
+                               //    one-gate-per-thread kernel at cfg3 (its loads are already coalesced and all issued before the first use)
 #endif
 
 template <int F>
@@ -311,6 +312,7 @@ __device__ __forceinline__ void emit_image(const ImageParams& im, size_t o, T v)
                 case RG_PF_BELOW: hit = v < a; break;
                 case RG_PF_ABOVE: hit = v > a; break;
                 case RG_PF_OUTSIDE: hit = (v < a) || (v > b); break;
+                case RG_PF_BELOW_EQUAL: hit = v <= a; break;
                 default: hit = isnan(v) || isinf(v); break;
             }
             if (hit) v = (T)im.fill[i];
@@ -336,13 +338,39 @@ __device__ __forceinline__ void emit_image(const ImageParams& im, size_t o, T v)
     im.out[o] = c;
 }
 
+// np.linspace(start, stop, num)[i] in float64 (arange * step + start, the last element is stop itself)
+__device__ __forceinline__ double linspace_f64(double start, double stop, int num, int i)
+{
+    if (num <= 1) return start;
+    if (i == num - 1) return stop;
+    return __dadd_rn(__dmul_rn((double)i, __ddiv_rn(__dsub_rn(stop, start), (double)(num - 1))), start);
+}
+
+// radar_processor's own PPI collapse (reference processor.py:513-528, utils.py:369-378): the level closest to
+// z_target = r sin(el) + r^2 / (2 * 8.49e6), r = sqrt(X^2 + Y^2) on the grid's float64 axes; argmin keeps the first
+// minimum; no out-of-grid masking.
+__device__ __forceinline__ int closest_level(const ProductParams& pp, const SliceParams& s, int64_t col)
+{
+    const int iy = (int)(col / pp.nx), ix = (int)(col - (int64_t)iy * pp.nx);
+    const double X = linspace_f64(pp.x_min, pp.x_max, pp.nx, ix), Y = linspace_f64(pp.y_min, pp.y_max, pp.ny, iy);
+    const double r = __dsqrt_rn(__dadd_rn(__dmul_rn(X, X), __dmul_rn(Y, Y)));
+    const double zt = __dadd_rn(__dmul_rn(r, s.sin_e), __ddiv_rn(__dmul_rn(r, r), 2.0 * 8.49e6));
+    int best = 0;
+    double best_d = fabs(__dsub_rn(zt, linspace_f64(pp.z_min, pp.z_max, pp.nz_full, 0)));
+    for (int k = 1; k < pp.nz_full; ++k) {
+        const double d = fabs(__dsub_rn(zt, linspace_f64(pp.z_min, pp.z_max, pp.nz_full, k)));
+        if (d < best_d) { best_d = d; best = k; }
+    }
+    return best;
+}
+
 struct ColumnState {
     float cmax, cmin, msum;
     int mcnt;
     float s_lo[RG_MAX_SLICES], s_hi[RG_MAX_SLICES];
     int zz[RG_MAX_SLICES];               // captured levels: lo | hi << 16
 
-    __device__ __forceinline__ void init(const ProductParams& pp, float x, float y)
+    __device__ __forceinline__ void init(const ProductParams& pp, float x, float y, int64_t col = 0)
     {
         cmax = cmin = __uint_as_float(kCanonNaN);
         msum = 0.f;
@@ -354,7 +382,9 @@ struct ColumnState {
             if (k < pp.n_slices) {
                 const SliceParams& s = pp.slices[k];
                 int lo, hi;
-                if (s.kind == RG_PROD_BEAM) {
+                if (s.kind == RG_PROD_BEAM && s.mode == 2) {
+                    lo = hi = closest_level(pp, s, col);
+                } else if (s.kind == RG_PROD_BEAM) {
                     const double tz = beam_target_z(s, x, y);
                     const double zf = __ddiv_rn(__dsub_rn(tz, pp.z_min), pp.z_step);
                     if (s.mode == 1) {           // 'nearest'  products.py:259-264
@@ -510,7 +540,9 @@ struct ColumnState {
                 const int lo = zz[k] & 0xFFFF, hi = zz[k] >> 16;
                 const bool own_lo = !s.partial || (lo >= pp.own_z0 && lo < pp.own_z1);
                 const bool own_hi = !s.partial || (hi >= pp.own_z0 && hi < pp.own_z1);
-                if (s.kind == RG_PROD_BEAM) {
+                if (s.kind == RG_PROD_BEAM && s.mode == 2) {
+                    put(s.out, s.image, own_lo ? s_lo[k] : -0.0f);
+                } else if (s.kind == RG_PROD_BEAM) {
                     const double tz = beam_target_z(s, x, y);
                     const double zf = __ddiv_rn(__dsub_rn(tz, pp.z_min), pp.z_step);
                     if (s.mode == 1) {
@@ -561,7 +593,7 @@ __global__ void __launch_bounds__(256) products_kernel(const __grid_constant__ P
     const float x = __ldg(p.prod.x_ax + (int)(col % p.nx));
     const float y = __ldg(p.prod.y_ax + (int)(col / p.nx));
     ColumnState st;
-    st.init(p.prod, x, y);
+    st.init(p.prod, x, y, col);
     const float* __restrict__ grid = p.grids[field];
     for (int lz = 0; lz < p.n_levels; ++lz) {
         const float v = __ldcs(grid + (size_t)lz * (size_t)p.ncol + (size_t)col);
@@ -955,7 +987,7 @@ __global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_ker
             y = __ldg(p.prod.y_ax + (int)(col / p.nx));
         }
         ColumnState st;
-        st.init(p.prod, x, y);
+        st.init(p.prod, x, y, col);
 #pragma unroll
         for (int k = 0; k < NO; ++k) st.store_words(p.prod, sm_state, k, NO);
         st.store_levels(p.prod, sm_state, NO);
@@ -1293,7 +1325,7 @@ __global__ void __launch_bounds__(kSellThreads) apply_sell_kernel(const __grid_c
             x = __ldg(p.prod.x_ax + (int)(col % p.nx));
             y = __ldg(p.prod.y_ax + (int)(col / p.nx));
         }
-        st.init(p.prod, x, y);
+        st.init(p.prod, x, y, col);
 #pragma unroll
         for (int f = 0; f < F; ++f) st.store_words(p.prod, sm_state, f, F);
         st.store_levels(p.prod, sm_state, F);
@@ -1514,6 +1546,68 @@ __global__ void __launch_bounds__(128) apply_reference_order_kernel(const __grid
         }
         out[row] = v;
     }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Nearest-gate gridding (the interpolation stage process_radar_to_cog asks Py-ART for: map_gates_to_grid with
+// weighting_function='nearest', reference processor.py:152-163).  The table was built with RG_W_DIST2, i.e. its weight
+// slot holds float32(d^2); per field a voxel takes the value of the closest gate whose value is not masked; among equal
+// distances the lowest gate id wins (Py-ART keeps the first gate of its scan that reaches the minimum, `dist2 <
+// min_dist2`).  One warp per row; not a fused path: the grid is written, products come from products_kernel.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) apply_nearest_kernel(const __grid_constant__ ApplyParams p, int64_t n_rows)
+{
+    constexpr unsigned kFull = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const uint32_t s = __ldg(p.indptr + row), e = __ldg(p.indptr + row + 1);
+    const int nf = p.n_fields;
+    const int fa = nf == 1 ? 1 : nf == 2 ? 2 : 4;
+    const int fb = nf <= 4 ? 0 : nf == 5 ? (RG_MASKBITS ? 2 : 1) : nf == 6 ? 2 : 4;
+    const bool mb = RG_MASKBITS && (nf == 3 || nf == 5 || nf == 7);
+    for (int f = 0; f < nf; ++f) {
+        float* out = p.grid_out[f];
+        if (out == nullptr) continue;
+        const float* rec = f < fa ? p.records : p.records_b;
+        const int stride = f < fa ? fa : fb, off = f < fa ? f : f - fa;
+        float best_d = __uint_as_float(0x7F800000u);          // +inf
+        uint32_t best_g = 0xFFFFFFFFu;
+        float best_v = 0.f;
+        for (uint32_t i = s + lane; i < e; i += 32) {
+            const uint2 pr = __ldg(p.pairs + i);
+            const float v = __ldg(rec + (size_t)pr.x * stride + off);
+            bool masked;
+            if (mb) {
+                const float* mrec = nf == 3 ? p.records : p.records_b;
+                const uint32_t bits = __float_as_uint(__ldg(mrec + (size_t)pr.x * (nf == 3 ? fa : fb) + (nf == 3 ? 3 : nf - fa)));
+                masked = (bits >> (f + (nf <= 5 ? 1 : 0))) & 1u;
+            } else {
+                masked = __float_as_uint(v) == kMaskedBits;
+            }
+            const float d = __uint_as_float(pr.y);
+            if (!masked && (d < best_d || (d == best_d && pr.x < best_g))) { best_d = d; best_g = pr.x; best_v = v; }
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            const float od = __shfl_xor_sync(kFull, best_d, o);
+            const uint32_t og = __shfl_xor_sync(kFull, best_g, o);
+            const float ov = __shfl_xor_sync(kFull, best_v, o);
+            if (og != 0xFFFFFFFFu && (best_g == 0xFFFFFFFFu || od < best_d || (od == best_d && og < best_g))) {
+                best_d = od; best_g = og; best_v = ov;
+            }
+        }
+        if (lane == 0) out[row] = best_g == 0xFFFFFFFFu ? p.fill : best_v;
+    }
+}
+
+int launch_apply_nearest(Context* ctx, const Geometry* g, const ApplyParams& p)
+{
+    if (g->n_rows == 0) return RG_OK;
+    apply_nearest_kernel<<<(unsigned)((g->n_rows + 3) / 4), 128, 0, ctx->stream>>>(p, g->n_rows);
+    ctx->launches++;
+    RG_CUDA(cudaGetLastError());
+    return RG_OK;
 }
 
 // ------------------------------------------------------------------------------------------------------

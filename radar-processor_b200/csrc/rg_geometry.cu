@@ -278,6 +278,7 @@ __device__ __forceinline__ float neighbour_weight(int weighting, double d2, doub
         return __double2float_rn(__dadd_rn(exp(__ddiv_rn(-d2, __ddiv_rn(r2, 4.0))), 1e-5));
     if (weighting == RG_W_CRESSMAN)       // compute.py:85
         return __double2float_rn(__ddiv_rn(__dsub_rn(r2, d2), __dadd_rn(r2, d2)));
+    if (weighting == RG_W_DIST2) return __double2float_rn(d2);     // nearest-gate tables carry the squared distance
     return 1.0f;                          // compute.py:87 ('nearest' = every gate in the ROI, weight 1)
 }
 

@@ -166,6 +166,8 @@ struct ProductParams {
     int32_t cmax_image, cmin_image, cmean_image, n_images;   // index into images, -1 = none
     ImageParams images[RG_MAX_IMAGES];
     double z_min, z_max, z_step;
+    double x_min, x_max, y_min, y_max;    // float64 axes of the closest-level beam product (BEAM mode 2)
+    int32_t nx, ny;
     const float* x_ax;
     const float* y_ax;
     SliceParams slices[RG_MAX_SLICES];
@@ -235,6 +237,7 @@ int records_width(int n_fields);          // floats per packed gate record: 1, 2
 size_t records_b_offset(int n_fields, int64_t n_gates);   // byte offset of array B inside the record buffer 
 int launch_pack(Context* ctx, const PackParams& p);
 int launch_apply(Context* ctx, const Geometry* g, const ApplyParams& p, bool reference_order);
+int launch_apply_nearest(Context* ctx, const Geometry* g, const ApplyParams& p);
 int launch_products(Context* ctx, const rg_grid_spec& grid, int n_fields, const float* const* grids_dev,
                     const ProductParams& prod);
 int build_geometry_device(Context* ctx, const float* gx, const float* gy, const float* gz, int64_t n_gates,

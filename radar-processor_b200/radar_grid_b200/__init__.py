@@ -22,6 +22,7 @@ from .products import (EARTH_RADIUS, EFFECTIVE_RADIUS_FACTOR, column_max, column
                        constant_altitude_ppi, constant_elevation_ppi, get_beam_height_difference,
                        get_elevation_from_z_level)
 from .geotiff import apply_colormap_to_array
+from . import adapter
 from .engine import (ImageSpec, colormap_lut_bytes, CAPPI, PPI, LevelPick, ColumnMax, ColumnMean, ColumnMin, DeviceGeometry, GeometryCache, RangeRule, VolumePipeline, grid_fields,
                      run_products)
 
@@ -38,6 +39,6 @@ __all__ = [
     # engine-level API
     "DeviceGeometry", "grid_fields", "run_products", "RangeRule", "VolumePipeline", "GeometryCache",
     "ColumnMax", "ColumnMin", "ColumnMean", "CAPPI", "PPI", "LevelPick", "ImageSpec", "colormap_lut_bytes",
-    "apply_colormap_to_array",
+    "apply_colormap_to_array", "adapter",
     "set_device", "get_device", "pinned_empty",
 ]

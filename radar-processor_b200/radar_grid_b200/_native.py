@@ -19,10 +19,10 @@ _PKG_ROOT = os.path.dirname(_HERE)
 
 RG_OK, RG_ERR_INVALID, RG_ERR_CUDA, RG_ERR_NOMEM, RG_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 RG_HOST, RG_DEVICE = 0, 1
-RG_W = {"barnes2": 0, "cressman": 1, "nearest": 2}
+RG_W = {"barnes2": 0, "cressman": 1, "nearest": 2, "dist2": 3}
 RG_PROD_COLMAX, RG_PROD_COLMIN, RG_PROD_COLMEAN, RG_PROD_LEVEL, RG_PROD_BEAM = 1, 2, 3, 4, 5
 RG_BLEND_PICK, RG_BLEND_F32, RG_BLEND_F64, RG_BLEND_F64_OUT64 = 0, 1, 2, 3
-RG_PF_BELOW, RG_PF_ABOVE, RG_PF_OUTSIDE, RG_PF_INVALID = 1, 2, 3, 4
+RG_PF_BELOW, RG_PF_ABOVE, RG_PF_OUTSIDE, RG_PF_INVALID, RG_PF_BELOW_EQUAL = 1, 2, 3, 4, 5
 RG_MAX_FIELDS, RG_MAX_RULES, RG_MAX_SLICES = 8, 8, 4
 
 

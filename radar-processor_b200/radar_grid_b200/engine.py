@@ -253,7 +253,8 @@ class ImageSpec:
         im = N.Image()
         im.n_filters = len(self.filters)
         for i, f in enumerate(self.filters):
-            kind = {"below": N.RG_PF_BELOW, "above": N.RG_PF_ABOVE, "outside": N.RG_PF_OUTSIDE, "invalid": N.RG_PF_INVALID}[f[0]]
+            kind = {"below": N.RG_PF_BELOW, "above": N.RG_PF_ABOVE, "outside": N.RG_PF_OUTSIDE, "invalid": N.RG_PF_INVALID,
+                    "below_equal": N.RG_PF_BELOW_EQUAL}[f[0]]
             im.filter_kind[i] = kind
             if kind == N.RG_PF_OUTSIDE:
                 im.filter_a[i], im.filter_b[i], im.filter_fill[i] = float(f[1]), float(f[2]), float(f[3]) if len(f) > 3 else np.nan
@@ -385,6 +386,10 @@ class PPI:
     name = "ppi"
 
     def resolve(self, grid_shape, grid_limits, have_geometry=True):
+        if self.interpolation == "closest_level":
+            # radar_processor's own collapse (processor.py:513-528): np.sin(np.deg2rad(elevation_deg)), Re = 8.49e6 in the kernel
+            return N.Product(kind=N.RG_PROD_BEAM, mode=2, partial=int(self.partial),
+                             sin_elev=float(np.sin(np.deg2rad(self.elevation_angle)))), np.float32
         if self.interpolation not in ("linear", "nearest"):
             raise ValueError(f"Unknown interpolation method: {self.interpolation}")
         elevation_rad = np.radians(self.elevation_angle)              # products.py:70
@@ -510,7 +515,7 @@ def run_products(grids: Sequence, grid_shape, grid_limits, products: Sequence, z
 def grid_fields(geom: DeviceGeometry, fields: Sequence, masks: Optional[Sequence] = None,
                 mask_invalid: Sequence[bool] | bool = False, rules: Sequence[RangeRule] = (),
                 fill_value: float = np.nan, want_grid: Sequence[bool] | bool = True, products: Sequence = (),
-                reference_order: bool = False, ctx: Optional[N.Context] = None,
+                reference_order=False, ctx: Optional[N.Context] = None,
                 out_grids: Optional[Sequence] = None, out_products: Optional[Sequence] = None) -> Dict[str, object]:
     """
     One fused pass over the neighbour table for ``len(fields)`` (<= 8) fields.
@@ -522,6 +527,8 @@ def grid_fields(geom: DeviceGeometry, fields: Sequence, masks: Optional[Sequence
     rules         RangeRule list, evaluated on the device and OR-ed into the masks (GateFilter fusion)
     want_grid     per-field flag: materialise the 3-D grid
     products      ColumnMax / ColumnMin / ColumnMean / CAPPI / PPI requests, fused in the epilogue
+    reference_order  False: fast fused path; True: the reference's summation order (bit-exact, un-fused);
+                  "nearest_gate": nearest-gate gridding on a table built with weighting="dist2" (adapter.py)
     out_grids / out_products  optional preallocated outputs (e.g. pinned host arrays) of the right shape/dtype
 
     Returns {"grids": [array or None per field], "products": [array (F, ny, nx) per request, None for an image-only
@@ -615,7 +622,7 @@ def grid_fields(geom: DeviceGeometry, fields: Sequence, masks: Optional[Sequence
     args.n_fields = F
     args.n_rules = len(rstructs)
     args.n_products = len(pstructs)
-    args.reference_order = int(bool(reference_order))
+    args.reference_order = 2 if reference_order == "nearest_gate" else int(bool(reference_order))
     args.mask_invalid_bits = inv_bits
     args.fill_value = float(fill_value)
     fptr = (C.c_void_p * F)(*[_ptr(f, device) for f in fheld])
