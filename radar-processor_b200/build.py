@@ -61,14 +61,22 @@ def build(force=False, variant="", extra_flags=(), verbose=False):
     from concurrent.futures import ThreadPoolExecutor
     flags = [f for f in NVCC_FLAGS if f != "-shared"] + list(extra_flags) + (["-Xptxas", "-v"] if verbose else [])
     with tempfile.TemporaryDirectory(prefix="rg_build_") as tmp:
-        objs = [os.path.join(tmp, os.path.basename(f)[:-3] + ".o") for f in SRC]
+        # rg_apply.cu is compiled as two translation units (field counts 1..4 + common code, and 5..8: see RG_PART there)
+        jobs = []
+        for f in SRC:
+            base = os.path.basename(f)[:-3]
+            if base == "rg_apply":
+                jobs += [(f, os.path.join(tmp, base + "_lo.o"), ["-DRG_PART=1"]), (f, os.path.join(tmp, base + "_hi.o"), ["-DRG_PART=2"])]
+            else:
+                jobs.append((f, os.path.join(tmp, base + ".o"), []))
+        objs = [j[1] for j in jobs]
 
         def compile_one(job):
-            src, obj = job
-            return subprocess.run([nvcc] + flags + ["-c", src, "-o", obj], capture_output=True, text=True)
+            src, obj, extra = job
+            return subprocess.run([nvcc] + flags + extra + ["-c", src, "-o", obj], capture_output=True, text=True)
 
-        with ThreadPoolExecutor(max_workers=len(SRC)) as pool:
-            results = list(pool.map(compile_one, zip(SRC, objs)))
+        with ThreadPoolExecutor(max_workers=len(jobs)) as pool:
+            results = list(pool.map(compile_one, jobs))
         for res in results:
             if res.returncode != 0:
                 sys.stderr.write(res.stdout + res.stderr)

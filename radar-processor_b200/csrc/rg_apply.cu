@@ -31,6 +31,18 @@
 
 namespace rg {
 
+// The kernels of this file are instantiated per field count (1..8); build.py compiles the file twice, in parallel:
+// RG_PART 1 = the common code and field counts 1..4, RG_PART 2 = field counts 5..8 only.  0 (the emulator build) = all.
+#ifndef RG_PART
+#define RG_PART 0
+#endif
+#define RG_LO (RG_PART != 2)
+#define RG_HI (RG_PART != 1)
+void launch_pack_hi(Context* ctx, const PackParams& p, bool vec);
+void launch_heavy_hi(Context* ctx, const ApplyParams& p);
+int launch_columns_hi(Context* ctx, const ApplyParams& p, int W);
+int launch_sell_hi(Context* ctx, const ApplyParams& p);
+
 // Build-time switches: every design decision of K5 can be re-measured (tools/gpu_ab.sh, build.py --variant X -DRG_...).
 #ifndef RG_PREFETCH
 #define RG_PREFETCH 1          // levels of look-ahead for the L2 prefetch of the pair stream (0 = off)
@@ -189,6 +201,7 @@ __global__ void __launch_bounds__(256) pack_records4_kernel(const __grid_constan
     }
 }
 
+#if RG_LO
 // (Re)create the texture objects over the record arrays when the buffer or the field count changed.
 int bind_record_textures(Context* ctx, const float* rec_a, const float* rec_b, int n_fields, int64_t n_gates)
 {
@@ -228,6 +241,8 @@ size_t records_b_offset(int n_fields, int64_t n_gates)
     return (((size_t)(n_gates + 1) * fa * sizeof(float)) + 511) & ~(size_t)511;   // texture-bindable
 }
 
+#endif  // RG_LO
+
 #ifndef RG_PACK4
 #define RG_PACK4 0             // 1: vector pack kernel (four gates per thread) when the pointers allow it; measured 46 vs 42 us for the
                                //    one-gate-per-thread kernel at cfg3 (its loads are already coalesced and all issued before the first use)
@@ -248,6 +263,19 @@ static void launch_pack_f(Context* ctx, const PackParams& p, bool vec)
     ctx->launches++;
 }
 
+#if RG_HI
+void launch_pack_hi(Context* ctx, const PackParams& p, bool vec)
+{
+    switch (p.n_fields) {
+        case 5: launch_pack_f<5>(ctx, p, vec); break;
+        case 6: launch_pack_f<6>(ctx, p, vec); break;
+        case 7: launch_pack_f<7>(ctx, p, vec); break;
+        default: launch_pack_f<8>(ctx, p, vec); break;
+    }
+}
+#endif
+
+#if RG_LO
 int launch_pack(Context* ctx, const PackParams& p)
 {
     bool vec = RG_PACK4 != 0;
@@ -260,15 +288,13 @@ int launch_pack(Context* ctx, const PackParams& p)
         case 2: launch_pack_f<2>(ctx, p, vec); break;
         case 3: launch_pack_f<3>(ctx, p, vec); break;
         case 4: launch_pack_f<4>(ctx, p, vec); break;
-        case 5: launch_pack_f<5>(ctx, p, vec); break;
-        case 6: launch_pack_f<6>(ctx, p, vec); break;
-        case 7: launch_pack_f<7>(ctx, p, vec); break;
-        default: launch_pack_f<8>(ctx, p, vec); break;
+        default: launch_pack_hi(ctx, p, vec); break;
     }
     timer_end(ctx, kTimerPack);
     RG_CUDA(cudaGetLastError());
     return RG_OK;
 }
+#endif  // RG_LO
 
 // ------------------------------------------------------------------------------------------------------
 // K6  per-column product state, shared by the fused epilogue and the stand-alone kernel so that both
@@ -577,6 +603,7 @@ struct ColumnState {
     }
 };
 
+#if RG_LO
 // Stand-alone products over existing grids: one thread per (column, field), coalesced along x.
 struct ProductsKernelParams {
     const float* grids[RG_MAX_FIELDS];
@@ -620,6 +647,8 @@ int launch_products(Context* ctx, const rg_grid_spec& grid, int n_fields, const 
     RG_CUDA(cudaGetLastError());
     return RG_OK;
 }
+
+#endif  // RG_LO
 
 // ------------------------------------------------------------------------------------------------------
 // K5  fast path: column-tile CSR gather, W lanes per column, products in the epilogue
@@ -1436,6 +1465,7 @@ __global__ void __launch_bounds__(kSellThreads) apply_sell_kernel(const __grid_c
 //     reduceat(seg) = a[0] + pairwise_sum(a[1:])   with NumPy's pairwise_sum: < 8 elements sequential,
 //     <= 128 eight interleaved accumulators, otherwise split at (n/2 rounded down to a multiple of 8).
 // ------------------------------------------------------------------------------------------------------
+#if RG_LO
 template <int FP>
 struct RowTerms {
     const uint2* pairs;
@@ -1610,6 +1640,8 @@ int launch_apply_nearest(Context* ctx, const Geometry* g, const ApplyParams& p)
     return RG_OK;
 }
 
+#endif  // RG_LO
+
 // ------------------------------------------------------------------------------------------------------
 // dispatch
 // ------------------------------------------------------------------------------------------------------
@@ -1667,6 +1699,45 @@ static int launch_sell(Context* ctx, const ApplyParams& p)
     return RG_OK;
 }
 
+template <int F>
+static void launch_heavy(Context* ctx, const ApplyParams& p)
+{
+    heavy_rows_kernel<F><<<(unsigned)p.n_heavy_chunks, kHeavyThreads, 0, ctx->stream>>>(p);
+}
+
+#if RG_HI
+void launch_heavy_hi(Context* ctx, const ApplyParams& p)
+{
+    switch (p.n_fields) {
+        case 5: launch_heavy<5>(ctx, p); break;
+        case 6: launch_heavy<6>(ctx, p); break;
+        case 7: launch_heavy<7>(ctx, p); break;
+        default: launch_heavy<8>(ctx, p); break;
+    }
+}
+
+int launch_columns_hi(Context* ctx, const ApplyParams& p, int W)
+{
+    switch (p.n_fields) {
+        case 5: return launch_columns_w<5>(ctx, p, W);
+        case 6: return launch_columns_w<6>(ctx, p, W);
+        case 7: return launch_columns_w<7>(ctx, p, W);
+        default: return launch_columns_w<8>(ctx, p, W);
+    }
+}
+
+int launch_sell_hi(Context* ctx, const ApplyParams& p)
+{
+    switch (p.n_fields) {
+        case 5: return launch_sell<5>(ctx, p);
+        case 6: return launch_sell<6>(ctx, p);
+        case 7: return launch_sell<7>(ctx, p);
+        default: return launch_sell<8>(ctx, p);
+    }
+}
+#endif  // RG_HI
+
+#if RG_LO
 // Pairs from the warp-slice copy?  It pays when the kernel is bound by instruction issue and the L1 data pipe (several
 // fields per pair); a single-field pass over a large table is HBM-bound and better off without the padding.
 static bool use_slices(const Context* ctx, int n_fields)
@@ -1695,12 +1766,6 @@ static int pick_group_width(const Context* ctx, const Geometry* g, int n_fields,
     return W;
 }
 
-template <int F>
-static void launch_heavy(Context* ctx, const ApplyParams& p)
-{
-    heavy_rows_kernel<F><<<(unsigned)p.n_heavy_chunks, kHeavyThreads, 0, ctx->stream>>>(p);
-}
-
 int launch_apply(Context* ctx, const Geometry* g, const ApplyParams& p, bool reference_order)
 {
     // An empty z-slab (z_begin == z_end: more ranks than levels) has no rows, but a fused products request must still
@@ -1727,10 +1792,7 @@ int launch_apply(Context* ctx, const Geometry* g, const ApplyParams& p, bool ref
             case 2: st = launch_sell<2>(ctx, p); break;
             case 3: st = launch_sell<3>(ctx, p); break;
             case 4: st = launch_sell<4>(ctx, p); break;
-            case 5: st = launch_sell<5>(ctx, p); break;
-            case 6: st = launch_sell<6>(ctx, p); break;
-            case 7: st = launch_sell<7>(ctx, p); break;
-            case 8: st = launch_sell<8>(ctx, p); break;
+            case 5: case 6: case 7: case 8: st = launch_sell_hi(ctx, p); break;
             default: return fail(RG_ERR_INVALID, "n_fields must be 1..8");
         }
         timer_end(ctx, kTimerApply);
@@ -1775,10 +1837,7 @@ int launch_apply(Context* ctx, const Geometry* g, const ApplyParams& p, bool ref
             case 2: launch_heavy<2>(ctx, q); break;
             case 3: launch_heavy<3>(ctx, q); break;
             case 4: launch_heavy<4>(ctx, q); break;
-            case 5: launch_heavy<5>(ctx, q); break;
-            case 6: launch_heavy<6>(ctx, q); break;
-            case 7: launch_heavy<7>(ctx, q); break;
-            case 8: launch_heavy<8>(ctx, q); break;
+            case 5: case 6: case 7: case 8: launch_heavy_hi(ctx, q); break;
             default: return fail(RG_ERR_INVALID, "n_fields must be 1..8");
         }
         ctx->launches++;
@@ -1788,10 +1847,7 @@ int launch_apply(Context* ctx, const Geometry* g, const ApplyParams& p, bool ref
         case 2: launch_columns_w<2>(ctx, q, W); break;
         case 3: launch_columns_w<3>(ctx, q, W); break;
         case 4: launch_columns_w<4>(ctx, q, W); break;
-        case 5: launch_columns_w<5>(ctx, q, W); break;
-        case 6: launch_columns_w<6>(ctx, q, W); break;
-        case 7: launch_columns_w<7>(ctx, q, W); break;
-        case 8: launch_columns_w<8>(ctx, q, W); break;
+        case 5: case 6: case 7: case 8: launch_columns_hi(ctx, q, W); break;
         default: return fail(RG_ERR_INVALID, "n_fields must be 1..8");
     }
     timer_end(ctx, kTimerApply);
@@ -1799,5 +1855,7 @@ int launch_apply(Context* ctx, const Geometry* g, const ApplyParams& p, bool ref
     RG_CUDA(cudaGetLastError());
     return RG_OK;
 }
+
+#endif  // RG_LO
 
 }  // namespace rg

@@ -818,9 +818,14 @@ int build_geometry_device(Context* ctx, const float* gx, const float* gy, const 
     cg.ncz = (int)floor(ez / cell) + 1;
     const int64_t ncell = (int64_t)cg.ncx * cg.ncy * cg.ncz;
 
-    cudaEvent_t ev0, ev1;
-    RG_CUDA(cudaEventCreate(&ev0));
-    RG_CUDA(cudaEventCreate(&ev1));
+    // the build's device time; destroyed on every exit path, the early error returns of RG_CUDA / RG_TRY included
+    struct EventPair {
+        cudaEvent_t a = nullptr, b = nullptr;
+        ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    } evs;
+    RG_CUDA(cudaEventCreate(&evs.a));
+    RG_CUDA(cudaEventCreate(&evs.b));
+    cudaEvent_t ev0 = evs.a, ev1 = evs.b;
     RG_CUDA(cudaEventRecord(ev0, ctx->stream));
 
     // ---- K1 binning
@@ -851,7 +856,6 @@ int build_geometry_device(Context* ctx, const float* gx, const float* gy, const 
     unsigned long long nonfinite = 0;
     RG_CUDA(cudaMemcpy(&nonfinite, counters.p, sizeof(nonfinite), cudaMemcpyDeviceToHost));
     if (nonfinite != 0) {
-        cudaEventDestroy(ev0); cudaEventDestroy(ev1);
         return fail(RG_ERR_INVALID, "data must be finite, check for nan or inf values (gate coordinates below toa)");
     }
     RG_CUDA(slot_ids.alloc((size_t)n_binned));
@@ -900,7 +904,6 @@ int build_geometry_device(Context* ctx, const float* gx, const float* gy, const 
         RG_CUDA(cudaStreamSynchronize(ctx->stream));
         const double scale = (double)ncol / (double)std::max<int64_t>(1, (int64_t)nxs * nys);
         for (int l = 0; l < n_levels; ++l) level_pairs_host[l] = (int64_t)llround((double)h[l] * scale);
-        cudaEventDestroy(ev0); cudaEventDestroy(ev1);
         return RG_OK;
     }
 
@@ -923,7 +926,6 @@ int build_geometry_device(Context* ctx, const float* gx, const float* gy, const 
     uint64_t n_pairs = 0;
     RG_TRY(exclusive_scan_u32(ctx, counts.p, out->indptr, n_rows, scan_tmp.p, &n_pairs));
     if (n_pairs >= 0xFFFFFFFFull) {
-        cudaEventDestroy(ev0); cudaEventDestroy(ev1);
         return fail(RG_ERR_UNSUPPORTED,
                     "neighbour table of this slab exceeds 2^32-1 pairs; split the grid into thinner z-slabs (z_begin/z_end)");
     }
@@ -946,8 +948,6 @@ int build_geometry_device(Context* ctx, const float* gx, const float* gy, const 
     RG_CUDA(cudaStreamSynchronize(ctx->stream));
     float ms = 0.f;
     RG_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
     unsigned long long cand = 0;
     RG_CUDA(cudaMemcpy(&cand, counters.p + 1, sizeof(cand), cudaMemcpyDeviceToHost));
 

@@ -418,6 +418,25 @@ def _as_f32_host(a) -> np.ndarray:
     return np.ascontiguousarray(np.asarray(a).ravel(), dtype=np.float32)
 
 
+def _check_buffer(x, device: bool, n: int, dtype, what: str):
+    """A caller-supplied buffer goes to the library as a raw pointer: refuse anything that is not exactly the C-contiguous
+    array of `n` elements of `dtype` on the side (host / device) the call runs on."""
+    if device:
+        import torch
+        want = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64, np.dtype(np.uint8): torch.uint8}[np.dtype(dtype)]
+        if not (hasattr(x, "is_cuda") and x.is_cuda):
+            raise ValueError(f"{what}: expected a CUDA tensor (the fields of this call are device buffers)")
+        ok_dtype = x.dtype == want or (want == torch.uint8 and x.dtype == torch.bool)
+        if not ok_dtype or not x.is_contiguous() or x.numel() != n:
+            raise ValueError(f"{what}: expected a contiguous {want} tensor of {n} elements, got {x.dtype} {tuple(x.shape)}"
+                             f"{'' if x.is_contiguous() else ' (not contiguous)'}")
+    else:
+        if N.is_device_array(x) or not isinstance(x, np.ndarray):
+            raise ValueError(f"{what}: expected a NumPy array (the fields of this call are host buffers)")
+        if x.dtype != np.dtype(dtype) or not x.flags.c_contiguous or x.size != n or not x.flags.writeable:
+            raise ValueError(f"{what}: expected a writable C-contiguous {np.dtype(dtype)} array of {n} elements, got {x.dtype} {x.shape}")
+
+
 def _alloc_like(device: bool, shape, dtype, ref=None):
     if not device:
         return np.empty(shape, dtype=dtype)
@@ -541,8 +560,11 @@ def grid_fields(geom: DeviceGeometry, fields: Sequence, masks: Optional[Sequence
     device = N.is_device_array(fields[0])
     G = geom.n_gates
     if device:
+        import torch
         fheld = [f.contiguous() for f in fields]
         for f in fheld:
+            if not (hasattr(f, "is_cuda") and f.is_cuda) or f.dtype != torch.float32:
+                raise ValueError("device fields must be float32 CUDA tensors (convert before the call: the library reads raw float32)")
             if f.numel() != G:
                 raise ValueError(f"field has {f.numel()} gates, geometry expects {G}")
     else:
@@ -557,6 +579,8 @@ def grid_fields(geom: DeviceGeometry, fields: Sequence, masks: Optional[Sequence
                 continue
             if device:
                 import torch
+                if not (hasattr(m, "is_cuda") and m.is_cuda) or m.dtype not in (torch.bool, torch.uint8) or m.numel() != G:
+                    raise ValueError("device masks must be bool / uint8 CUDA tensors with one entry per gate")
                 mheld[i] = m.contiguous().view(torch.uint8) if m.dtype == torch.bool else m.contiguous()
             else:
                 mheld[i] = np.ascontiguousarray(np.asarray(m).ravel()).astype(np.uint8, copy=False) \
@@ -576,8 +600,7 @@ def grid_fields(geom: DeviceGeometry, fields: Sequence, masks: Optional[Sequence
             grids.append(None)
         elif out_grids is not None and out_grids[i] is not None:
             g = out_grids[i]
-            if int(np.prod(g.shape)) != nzs * ny * nx:
-                raise ValueError("out_grids entry has the wrong size")
+            _check_buffer(g, device, nzs * ny * nx, np.float32, f"out_grids[{i}]")
             grids.append(g)
         else:
             grids.append(_alloc_like(device, (nzs, ny, nx), np.float32, fheld[0]))
@@ -604,6 +627,7 @@ def grid_fields(geom: DeviceGeometry, fields: Sequence, masks: Optional[Sequence
         img_spec = getattr(p, "image", None)
         if out_products is not None and out_products[k] is not None:
             out = out_products[k]
+            _check_buffer(out, device, F * ny * nx, dt, f"out_products[{k}] ({type(p).__name__}: {np.dtype(dt)})")
         elif img_spec is not None and not img_spec.keep_plane:
             out = None
         else:

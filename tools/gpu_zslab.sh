@@ -1,7 +1,13 @@
 #!/bin/bash
+# One GPU: the z-slab example checked against the unsharded build (cfg3), then BASELINE configs[4] (cfg5) slab by slab,
+# with slabs of equal level count (round-1 layout, for comparison) and balanced by pair count.
 set -u
 mkdir -p gpurun_out
-echo "== device-buffer tests"; timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider -k "device_buffers or zslab or pipeline" 2>&1 | tail -2
-echo "== small, 3 slabs, checked against the unsharded build"; timeout 300 python examples/zslab_colmax.py --spec small --slabs 3 --check 2>&1 | tail -1 | cut -c1-300
-echo "== cfg3, 4 slabs, checked"; timeout 300 python examples/zslab_colmax.py --spec cfg3 --slabs 4 --check 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print({k:d[k] for k in d if k!='per_slab'})"
-echo "== cfg5, 8 slabs on one GPU in sequence"; timeout 1200 python examples/zslab_colmax.py --spec cfg5 --slabs 8 > gpurun_out/zslab_cfg5.json 2> gpurun_out/zslab_cfg5.err; echo "exit $?"; cut -c1-2500 gpurun_out/zslab_cfg5.json; tail -3 gpurun_out/zslab_cfg5.err
+F='import sys,json
+for l in sys.stdin:
+    if l.startswith("{"):
+        d=json.loads(l); print(json.dumps({k:d[k] for k in d if k not in ("per_slab_rank0",)})); [print("   ", s) for s in d["per_slab_rank0"]]'
+echo "== adapter + new tests"; timeout 600 python -m pytest tests/test_adapter.py tests/test_gpu_configs.py -m gpu -q -p no:cacheprovider -x --deselect tests/test_gpu_configs.py::test_cfg5_slab_rows_against_bruteforce_and_colmax_against_the_oracle 2>&1 | tail -3
+echo "== cfg3, 4 balanced slabs, COLMAX + CAPPI + PPI, checked"; timeout 300 python examples/zslab_colmax.py --spec cfg3 --slabs 4 --cappi 4750 --ppi 1.0 --check 2>gpurun_out/zslab_cfg3.err | tee gpurun_out/zslab_cfg3_1gpu.json | python -c "$F"; tail -2 gpurun_out/zslab_cfg3.err
+echo "== cfg5, 8 slabs of equal level count (split where > 2^32 pairs)"; timeout 900 python examples/zslab_colmax.py --spec cfg5 --slabs 8 --even 2>gpurun_out/zslab_cfg5_even.err | tee gpurun_out/zslab_cfg5_even_1gpu.json | python -c "$F"; tail -2 gpurun_out/zslab_cfg5_even.err
+echo "== cfg5, 8 slabs balanced by pair count"; timeout 900 python examples/zslab_colmax.py --spec cfg5 --slabs 8 2>gpurun_out/zslab_cfg5_bal.err | tee gpurun_out/zslab_cfg5_balanced_1gpu.json | python -c "$F"; tail -2 gpurun_out/zslab_cfg5_bal.err
