@@ -348,7 +348,10 @@ def zslab_record(rg, N, S, spec, gates, raw, dev, ctx, world, rank, local_rank):
     pair count (level census, DeviceGeometry.level_pairs), every rank builds and grids only its slab (COLMAX + CAPPI
     4000 m as fused z-slab terms, no 3-D grid) and ONE all-reduce(MAX) + ONE all-reduce(SUM) over NCCL finish the
     planes.  Reported: wall ms per volume including the collectives (max over ranks), the collectives alone, the
-    unsharded products-only pass on one GPU, and whether the planes are bit-identical to the unsharded ones.
+    unsharded products-only pass on one GPU, and whether the planes are bit-identical to the unsharded ones.  (A cfg3
+    volume takes 0.66 ms on ONE GPU: the two collectives and the host-side call overhead weigh as much as the kernels, so
+    this record shows what the exchange costs rather than a speed-up; the shard is meant for grids like cfg5, see
+    examples/zslab_colmax.py.)
     """
     import torch
     import torch.distributed as dist
@@ -362,7 +365,8 @@ def zslab_record(rg, N, S, spec, gates, raw, dev, ctx, world, rank, local_rank):
     slab = rg.DeviceGeometry.build(*gates, spec.grid_shape, spec.grid_limits, weighting=spec.weighting, z_range=ranges[rank], ctx=ctx, **kw)
     build_s = time.perf_counter() - t0
     products = [rg.ColumnMax(), rg.CAPPI(CAPPI_ALT)]
-    stream = torch.cuda.current_stream()
+    if rank != 0:
+        _, raw = raw_fields(spec, seed=0, gates=gates)        # a z-slab shard grids ONE volume: rank 0's, on every rank
     dfields = [torch.from_numpy(r).cuda() for r in raw]
     ctx.set_option("group_width", 4)                       # same summation order for the slabs and the unsharded table
     try:
@@ -370,6 +374,8 @@ def zslab_record(rg, N, S, spec, gates, raw, dev, ctx, world, rank, local_rank):
         got = D.zslab_products(slab, dfields, products, mask_invalid=True, ctx=ctx)
         identical = all(torch.equal(a.nan_to_num(-1e30), b.nan_to_num(-1e30)) for a, b in zip(got, want))
         reps, wall, coll, apply_ms = 20, [], [], []
+        ctx.kernel_time(0), ctx.kernel_time(1)                # reset the per-kernel device timers
+        ctx.set_option("timing", 1)
         for _ in range(3 + reps):
             dist.barrier()
             torch.cuda.synchronize()
@@ -380,6 +386,8 @@ def zslab_record(rg, N, S, spec, gates, raw, dev, ctx, world, rank, local_rank):
             wall.append((time.perf_counter() - t0) * 1e3)
             coll.append(tm["allreduce_ms"])
             apply_ms.append(tm["apply_ms"])
+        ctx.set_option("timing", 0)
+        dev_ms = (ctx.kernel_time(0)[0] + ctx.kernel_time(1)[0]) / (3 + reps)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(reps):
@@ -389,7 +397,7 @@ def zslab_record(rg, N, S, spec, gates, raw, dev, ctx, world, rank, local_rank):
     finally:
         ctx.set_option("group_width", int(os.environ.get("RG_GROUP_WIDTH") or 0))
     stats = torch.tensor([float(np.median(wall[3:])), float(np.median(coll[3:])), float(np.median(apply_ms[3:])), build_s,
-                          float(slab.n_pairs), float(identical)], dtype=torch.float64, device="cuda")
+                          float(slab.n_pairs), float(identical), dev_ms], dtype=torch.float64, device="cuda")
     allr = [torch.zeros_like(stats) for _ in range(world)]
     dist.all_gather(allr, stats)
     allr = torch.stack(allr).cpu().numpy()
@@ -397,7 +405,9 @@ def zslab_record(rg, N, S, spec, gates, raw, dev, ctx, world, rank, local_rank):
     return {"what": f"{spec.name} in {world} z-slabs balanced by pair count, COLMAX + CAPPI {CAPPI_ALT:.0f} m as fused z-slab terms, "
                     "all-reduce(MAX) + all-reduce(SUM) over NCCL; wall clock per volume incl. the collectives, median of 20",
             "slab_levels": [list(r) for r in ranges], "slab_pairs": [int(v) for v in allr[:, 4]],
-            "wall_ms": float(allr[:, 0].max()), "allreduce_ms": float(allr[:, 1].max()), "slab_apply_ms_per_rank": [float(v) for v in allr[:, 2]],
+            "wall_ms": float(allr[:, 0].max()), "allreduce_ms": float(allr[:, 1].max()),
+            "slab_apply_wall_ms_per_rank": [float(v) for v in allr[:, 2]],
+            "slab_kernels_device_ms_per_rank": [float(v) for v in allr[:, 6]],
             "slab_build_s_per_rank": [float(v) for v in allr[:, 3]], "unsharded_ms_one_gpu": unsharded_ms,
             "speedup_vs_one_gpu": unsharded_ms / float(allr[:, 0].max()), "identical": bool(allr[:, 5].min() == 1.0)}
 

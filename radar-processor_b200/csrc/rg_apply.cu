@@ -963,8 +963,11 @@ __global__ void __launch_bounds__(kHeavyThreads) heavy_rows_kernel(const __grid_
 // "COLMAX and/or one level pick/blend (CAPPI)" with its three state words in registers.
 // IL: the pairs come from the warp-slice copy of the table (one coalesced 256-byte load per slot, no per-lane row
 // bounds, the slot count of a level is warp-uniform) instead of the CSR copy.
+#ifndef RG_MINBLOCKS_F1
+#define RG_MINBLOCKS_F1 RG_MINBLOCKS   // CTAs per SM asked of the ONE-field kernel: 10 (48 registers, no spills, 40 warps) is the candidate
+#endif
 template <int F, int W, int PSIG, bool IL>
-__global__ void __launch_bounds__(kApplyThreads, RG_MINBLOCKS) apply_columns_kernel(const __grid_constant__ ApplyParams p)
+__global__ void __launch_bounds__(kApplyThreads, F == 1 ? RG_MINBLOCKS_F1 : RG_MINBLOCKS) apply_columns_kernel(const __grid_constant__ ApplyParams p)
 {
     constexpr bool PROD = PSIG == 1;
     static_assert(!IL || RG_TILE2D == 1, "the warp-slice copy assumes the groups of a warp are adjacent in x");
