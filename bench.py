@@ -118,7 +118,7 @@ class ClockSampler:
                         self.reasons.add(n)
             except Exception:
                 pass
-            self._stop.wait(0.01)
+            self._stop.wait(0.002)
 
     def start(self):
         if self._nv is not None:
@@ -592,7 +592,7 @@ def main():
         with _QuietStdout():
             line = run_reference(args)
     else:
-        args.steps = 200 if args.steps is None else max(1, args.steps)
+        args.steps = 300 if args.steps is None else max(1, args.steps)
         args.warmup = 10 if args.warmup is None else max(3, args.warmup)
         with _QuietStdout():
             line = run_b200(args)
