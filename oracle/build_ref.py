@@ -4,10 +4,11 @@ Recipe for oracle/_ref: the reference's OWN gridding modules, compiled from wher
 
 The reference's hot path is six pure-Python modules (src/radar_grid/{geometry,compute,interpolate,products,filters,
 utils}.py).  "Compiling" them means byte-compiling: this script runs ``py_compile`` on the sources under
-/root/reference and writes only the resulting ``.pyc`` files to ``oracle/_ref/radar_grid_ref/`` — build output, like a
-.so: git-ignored, never the sources themselves, but it travels to the GPU box with the gpurun snapshot (same image,
-same CPython), where /root/reference does not exist.  ``load()`` imports them as a package, without the reference's
-``__init__`` (which needs matplotlib / rasterio).
+/root/reference and writes only the resulting byte code to ``oracle/_ref/radar_grid_ref/<module>.rgc`` — build output,
+like a .so: git-ignored, never the sources themselves, but it travels to the GPU box with the gpurun snapshot (same
+image, same CPython), where /root/reference does not exist.  (The files are ordinary ``.pyc`` files under another
+suffix: snapshot tools tend to drop ``*.pyc``.)  ``load()`` imports them as a package with a sourceless loader, without
+the reference's ``__init__`` (which needs matplotlib / rasterio).
 
 Users: tests (to cross-check the NumPy restatement in radar_grid_oracle.py) and ``bench.py --impl reference`` (to time
 the genuine reference code on the box's host cores, ``cpu_baseline.kind = "reference"``).  TEST INFRASTRUCTURE ONLY.
@@ -32,7 +33,7 @@ def build() -> bool:
         return False
     os.makedirs(OUT, exist_ok=True)
     for name in MODULES:
-        py_compile.compile(os.path.join(REF_SRC, name + ".py"), cfile=os.path.join(OUT, name + ".pyc"),
+        py_compile.compile(os.path.join(REF_SRC, name + ".py"), cfile=os.path.join(OUT, name + ".rgc"),
                            dfile=f"reference/src/radar_grid/{name}.py", doraise=True)
     with open(os.path.join(OUT, "PYTHON_TAG"), "w") as fh:
         fh.write(sys.implementation.cache_tag)
@@ -45,17 +46,39 @@ def available() -> bool:
             tag = fh.read().strip()
     except OSError:
         return False
-    return tag == sys.implementation.cache_tag and all(os.path.exists(os.path.join(OUT, m + ".pyc")) for m in MODULES)
+    return tag == sys.implementation.cache_tag and all(os.path.exists(os.path.join(OUT, m + ".rgc")) for m in MODULES)
 
 
 def load():
     """The reference modules as a namespace (``ref.compute.compute_grid_geometry`` ...), from oracle/_ref."""
     if not available():
         raise RuntimeError("oracle/_ref is missing or was built by another CPython: run oracle/build_ref.py in the build container")
+    import importlib.machinery
+    import importlib.util
     pkg = types.ModuleType("radar_grid_ref")
     pkg.__path__ = [OUT]
     sys.modules["radar_grid_ref"] = pkg
-    return types.SimpleNamespace(**{m: importlib.import_module(f"radar_grid_ref.{m}") for m in MODULES})
+    mods, todo = {}, list(MODULES)
+    for _ in range(len(MODULES) + 1):          # the modules import one another relatively: load until all resolve
+        for name in list(todo):
+            full = f"radar_grid_ref.{name}"
+            loader = importlib.machinery.SourcelessFileLoader(full, os.path.join(OUT, name + ".rgc"))
+            spec = importlib.util.spec_from_loader(full, loader)
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[full] = mod
+            try:
+                loader.exec_module(mod)
+            except ImportError:
+                del sys.modules[full]
+                continue
+            setattr(pkg, name, mod)
+            mods[name] = mod
+            todo.remove(name)
+        if not todo:
+            break
+    if todo:
+        raise RuntimeError(f"could not import reference modules {todo} from oracle/_ref")
+    return types.SimpleNamespace(**mods)
 
 
 if __name__ == "__main__":

@@ -56,6 +56,11 @@ def build(force=False, variant="", extra_flags=(), verbose=False):
         if os.path.exists(out):
             return out          # GPU box without the sources' toolchain: use the shipped binary
         raise RuntimeError("nvcc not found and no prebuilt libradargrid_b200.so")
+    if not force and os.path.exists(out) and os.environ.get("GRAFT_REPO_ROOT") and not os.environ.get("RADAR_GRID_B200_REBUILD"):
+        # on a leased GPU box the shipped binary is what was meant to run: rebuilding ~190 kernels there would burn five
+        # GPU-minutes.  Say so loudly instead; build before taking the snapshot (or set RADAR_GRID_B200_REBUILD=1).
+        sys.stderr.write(f"radar_grid_b200: {out} is older than its sources; using it as shipped (GPU box)\n")
+        return out
     # one nvcc per source file, in parallel (rg_apply.cu alone instantiates ~190 kernels), then one link step
     import tempfile
     from concurrent.futures import ThreadPoolExecutor

@@ -60,6 +60,12 @@ int launch_sell_hi(Context* ctx, const ApplyParams& p);
 #define RG_TEX 0               // 1: gather the gate records through the texture path (tex1Dfetch) instead of LDG
 #endif
 
+#ifndef RG_PDL
+#define RG_PDL 1               // heavy_rows_kernel -> column kernel chained by programmatic dependent launch
+#endif
+#ifndef RG_PRELOAD
+#define RG_PRELOAD 0           // pairs of the next level's row preloaded into registers by one- and two-field passes over the CSR copy
+#endif
 #ifndef RG_MASKBITS
 #define RG_MASKBITS 0          // 1: odd field counts keep a mask-bit word in the free record slot (see Layout): packed FFMA2 value sums
                                //    and R2P predicates, 14 % fewer instructions -- and 16 % SLOWER (0.768 vs 0.663 ms): the kernel is
@@ -931,6 +937,9 @@ __global__ void __launch_bounds__(kHeavyThreads) heavy_rows_kernel(const __grid_
 {
     constexpr unsigned kFull = 0xFFFFFFFFu;
     __shared__ float part[kHeavyThreads / 32][2 * F];
+#if RG_PDL && !defined(RG_EMU)
+    asm volatile("griddepcontrol.launch_dependents;");           // the column kernel may start now; it waits only where it needs us
+#endif
     const uint2 ch = __ldg(p.heavy_chunks + blockIdx.x);
     const RecSrc rec{p.records, p.records_b, p.tex_a, p.tex_b, p.null_gate};
     float swv[F], sw[F];
@@ -1059,6 +1068,16 @@ __global__ void __launch_bounds__(kApplyThreads, F == 1 ? RG_MINBLOCKS_F1 : RG_M
     bounds(bp, p.lz_first, s_next, e_next);
     bounds(bp + bstride, p.lz_first + 1, s_next2, e_next2);
     bp += 2 * bstride;                                         // bounds of the level two ahead of the loop variable
+    // Narrow passes over the CSR copy (one or two fields: few registers, short rows, latency-bound) keep the first NP
+    // pairs of the NEXT level's row in registers, loaded while the current level is summed: the dependent chain of a
+    // level shrinks from pairs -> records to records only.
+    constexpr int NP = (!IL && F <= 2) ? RG_PRELOAD : 0;
+    uint2 pre[NP > 0 ? NP : 1];
+    if constexpr (NP > 0) {
+#pragma unroll
+        for (int j = 0; j < NP; ++j)
+            pre[j] = s_next + gl + j * W < e_next ? __ldcs(pairs + s_next + gl + j * W) : make_uint2(rec.null_gate, 0u);
+    }
 
     size_t row = (size_t)p.lz_first * (size_t)p.ncol + (size_t)col - (size_t)p.ncol;
     for (int lz = p.lz_first; lz < p.lz_last; ++lz) {
@@ -1068,6 +1087,14 @@ __global__ void __launch_bounds__(kApplyThreads, F == 1 ? RG_MINBLOCKS_F1 : RG_M
         e_next = e_next2;
         bounds(bp, lz + 2, s_next2, e_next2);
         bp += IL ? (size_t)p.ny * (size_t)p.quads_x : (size_t)p.ncol;
+        uint2 cur[NP > 0 ? NP : 1];
+        if constexpr (NP > 0) {
+#pragma unroll
+            for (int j = 0; j < NP; ++j) cur[j] = pre[j];
+#pragma unroll
+            for (int j = 0; j < NP; ++j)
+                pre[j] = s_next + gl + j * W < e_next ? __ldcs(pairs + s_next + gl + j * W) : make_uint2(rec.null_gate, 0u);
+        }
 #if RG_PREFETCH > 0
         if constexpr (IL) {   // level z+1's slots are contiguous: one 128-byte line per lane
             const uint32_t l0 = (s_next >> 1) * 2u + (uint32_t)lane;
@@ -1103,6 +1130,9 @@ __global__ void __launch_bounds__(kApplyThreads, F == 1 ? RG_MINBLOCKS_F1 : RG_M
             if constexpr (W < 32) {
                 // heavy rows were summed by heavy_rows_kernel: the group's first lane adds up the chunks' partial sums
                 if (heavy_mine && gl == 0) {
+#if RG_PDL && !defined(RG_EMU)
+                    asm volatile("griddepcontrol.wait;" ::: "memory");   // heavy_rows_kernel complete, its sums visible
+#endif
                     const uint32_t r32 = (uint32_t)row;
                     int lo = 0, hi = p.n_heavy - 1;
                     while (lo < hi) {                              // sorted list of a few hundred rows at most
@@ -1113,7 +1143,7 @@ __global__ void __launch_bounds__(kApplyThreads, F == 1 ? RG_MINBLOCKS_F1 : RG_M
                     for (uint32_t c = c0; c < c1; ++c) {
                         const float* hp = p.heavy_part + (size_t)c * (2 * F);
 #pragma unroll
-                        for (int f = 0; f < F; ++f) { swv[f] += hp[f]; sw[f] += hp[F + f]; }
+                        for (int f = 0; f < F; ++f) { swv[f] += __ldcg(hp + f); sw[f] += __ldcg(hp + F + f); }   // L2: written by the heavy kernel
                     }
                 }
             } else {
@@ -1142,7 +1172,7 @@ __global__ void __launch_bounds__(kApplyThreads, F == 1 ? RG_MINBLOCKS_F1 : RG_M
 #pragma unroll
                     for (int j = 0; j < M; ++j) {
                         if constexpr (IL) hp[j] = __ldcs(il_base + j * 32);
-                        else hp[j] = (uint32_t)j < need ? __ldcs(pairs + s + gl + j * W) : make_uint2(rec.null_gate, 0u);
+                        else hp[j] = (uint32_t)j < need ? (j < NP ? cur[j < NP ? j : 0] : __ldcs(pairs + s + gl + j * W)) : make_uint2(rec.null_gate, 0u);
                     }
                     constexpr int C0 = M < U ? M : U;
                     {
@@ -1648,6 +1678,32 @@ int launch_apply_nearest(Context* ctx, const Geometry* g, const ApplyParams& p)
 // ------------------------------------------------------------------------------------------------------
 // dispatch
 // ------------------------------------------------------------------------------------------------------
+// Launch the column kernel.  When heavy_rows_kernel was launched just before it, the two are chained by programmatic
+// dependent launch: the heavy kernel lets its dependents start right away (griddepcontrol.launch_dependents) and only the
+// few groups that pick up a heavy row's partial sums wait for it (griddepcontrol.wait), so its ~10 us of latency-bound
+// work run under the column kernel instead of in front of it.
+template <typename K>
+static void launch_column_kernel(K kernel, unsigned blocks, size_t smem, Context* ctx, const ApplyParams& p)
+{
+#if RG_PDL && !defined(RG_EMU)
+    if (p.n_heavy_chunks > 0) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(blocks);
+        cfg.blockDim = dim3(kApplyThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = ctx->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, kernel, p);
+        return;
+    }
+#endif
+    kernel<<<blocks, kApplyThreads, smem, ctx->stream>>>(p);
+}
+
 template <int F, int W>
 static void launch_columns(Context* ctx, const ApplyParams& p)
 {
@@ -1666,15 +1722,15 @@ static void launch_columns(Context* ctx, const ApplyParams& p)
     const size_t smem2 = RG_QSMEM && NO > 1 ? (size_t)3 * NO * kApplyThreads * sizeof(float) : 0;   // PSIG 2 state (QS)
     if (p.quads != nullptr) {
 #if RG_TILE2D
-        if (!pp.any) apply_columns_kernel<F, W, 0, true><<<blocks, kApplyThreads, 0, ctx->stream>>>(p);
-        else if (simple) apply_columns_kernel<F, W, 2, true><<<blocks, kApplyThreads, smem2, ctx->stream>>>(p);
-        else apply_columns_kernel<F, W, 1, true><<<blocks, kApplyThreads, smem, ctx->stream>>>(p);
+        if (!pp.any) launch_column_kernel(apply_columns_kernel<F, W, 0, true>, blocks, 0, ctx, p);
+        else if (simple) launch_column_kernel(apply_columns_kernel<F, W, 2, true>, blocks, smem2, ctx, p);
+        else launch_column_kernel(apply_columns_kernel<F, W, 1, true>, blocks, smem, ctx, p);
         return;
 #endif
     }
-    if (!pp.any) apply_columns_kernel<F, W, 0, false><<<blocks, kApplyThreads, 0, ctx->stream>>>(p);
-    else if (simple) apply_columns_kernel<F, W, 2, false><<<blocks, kApplyThreads, smem2, ctx->stream>>>(p);
-    else apply_columns_kernel<F, W, 1, false><<<blocks, kApplyThreads, smem, ctx->stream>>>(p);
+    if (!pp.any) launch_column_kernel(apply_columns_kernel<F, W, 0, false>, blocks, 0, ctx, p);
+    else if (simple) launch_column_kernel(apply_columns_kernel<F, W, 2, false>, blocks, smem2, ctx, p);
+    else launch_column_kernel(apply_columns_kernel<F, W, 1, false>, blocks, smem, ctx, p);
 }
 
 template <int F>
