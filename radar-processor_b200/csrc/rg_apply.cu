@@ -61,10 +61,12 @@ int launch_sell_hi(Context* ctx, const ApplyParams& p);
 #endif
 
 #ifndef RG_PDL
-#define RG_PDL 1               // heavy_rows_kernel -> column kernel chained by programmatic dependent launch
+#define RG_PDL 1               // heavy_rows_kernel -> column kernel chained by programmatic dependent launch (cfg3 0.659 -> 0.650 ms,
+                               //    cfg1 0.0525 -> 0.0465 ms)
 #endif
 #ifndef RG_PRELOAD
-#define RG_PRELOAD 0           // pairs of the next level's row preloaded into registers by one- and two-field passes over the CSR copy
+#define RG_PRELOAD 0           // N > 0: one- and two-field passes over the CSR copy keep the first N pairs of the NEXT level's row in
+                               //    registers.  Measured with N = 3: cfg1 0.0466 vs 0.0465 ms, one field of cfg3 0.565 vs 0.540 ms: off.
 #endif
 #ifndef RG_MASKBITS
 #define RG_MASKBITS 0          // 1: odd field counts keep a mask-bit word in the free record slot (see Layout): packed FFMA2 value sums

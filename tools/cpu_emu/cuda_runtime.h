@@ -116,6 +116,7 @@ inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 template <typename T> inline T __ldg(const T* p) { return *p; }
 template <typename T> inline T __ldcs(const T* p) { return *p; }
+template <typename T> inline T __ldcg(const T* p) { return *p; }
 template <typename T> inline void __stcs(T* p, T v) { *p = v; }
 template <typename T> inline T max(T a, T b) { return a > b ? a : b; }
 template <typename T> inline T min(T a, T b) { return a < b ? a : b; }
