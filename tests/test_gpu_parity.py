@@ -561,3 +561,32 @@ def test_zslab_fused_terms_of_every_product_kind_merge_to_the_unsharded_products
     finally:
         whole.grid_limits = spec.grid_limits
         whole.ctx.set_option("group_width", 0)
+
+
+def test_caller_buffers_are_validated_not_reinterpreted():
+    """out_grids / out_products / device fields and masks reach the library as raw pointers: anything that is not
+    exactly the contiguous array of the right dtype, size and side must raise instead of being read as something else."""
+    import torch
+    spec, radar, gates, fields, g = golden_case("tiny")
+    dev = build(spec, gates, "barnes2", 0)
+    name = list(fields)[0]
+    data, mask = np.ma.getdata(fields[name]), np.ma.getmaskarray(fields[name])
+    nz, ny, nx = spec.grid_shape
+    ok = rg.grid_fields(dev, [data], masks=[mask], out_grids=[np.empty((nz, ny, nx), np.float32)],
+                        products=[rg.PPI(2.3)], out_products=[np.empty((1, ny, nx), np.float64)])
+    assert ok["products"][0].dtype == np.float64
+    for bad in (np.empty((nz, ny, nx), np.float64), np.empty((nz, ny, 2 * nx), np.float32)[:, :, ::2], np.empty((nz, ny, nx - 1), np.float32),
+                torch.empty((nz, ny, nx), dtype=torch.float32, device="cuda")):
+        with pytest.raises(ValueError):
+            rg.grid_fields(dev, [data], masks=[mask], out_grids=[bad])
+    with pytest.raises(ValueError):                                          # PPI 'linear' planes are float64
+        rg.grid_fields(dev, [data], masks=[mask], products=[rg.PPI(2.3)], out_products=[np.empty((1, ny, nx), np.float32)])
+    d_data = torch.from_numpy(data).cuda()
+    with pytest.raises(ValueError):
+        rg.grid_fields(dev, [d_data.double()])
+    with pytest.raises(ValueError):
+        rg.grid_fields(dev, [d_data], masks=[torch.from_numpy(mask).cuda()[:-1]])
+    with pytest.raises(ValueError):
+        rg.grid_fields(dev, [d_data], out_grids=[np.empty((nz, ny, nx), np.float32)])
+    out = rg.grid_fields(dev, [d_data], masks=[torch.from_numpy(mask).cuda()])["grids"][0]
+    assert_same(out.cpu().numpy(), ok["grids"][0])
