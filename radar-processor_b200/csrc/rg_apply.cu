@@ -1799,14 +1799,18 @@ int launch_sell_hi(Context* ctx, const ApplyParams& p)
 #endif  // RG_HI
 
 #if RG_LO
-// Pairs from the warp-slice copy?  It pays when the kernel is bound by instruction issue and the L1 data pipe (several
-// fields per pair); a single-field pass over a large table is HBM-bound and better off without the padding.
-static bool use_slices(const Context* ctx, int n_fields)
+// Pairs from the warp-slice copy?  It pays when the kernel is bound by instruction issue and the L1 data pipe: several
+// fields per pair, or one field over short rows (cfg1: rows of 16 pairs, 0.0439 vs 0.0466 ms: the per-lane bounds and
+// votes of the CSR path weigh as much as the sums there).  A single-field pass over long rows (cfg5) is HBM-bound and
+// better off without the padding and the second copy of a table that fills the GPU.
+static bool use_slices(const Context* ctx, const Geometry* g, int n_fields)
 {
 #if RG_TILE2D && RG_HEADBATCH == 2
     if (ctx->apply_variant == 4) return true;
     if (ctx->apply_variant == 1) return false;
-    return n_fields >= 2;
+    if (n_fields >= 2) return true;
+    const int64_t nonempty = g->info.n_rows - g->info.n_empty_rows;
+    return nonempty > 0 && (double)g->info.n_pairs / (double)nonempty < 24.0;
 #else
     return false;
 #endif
@@ -1862,7 +1866,7 @@ int launch_apply(Context* ctx, const Geometry* g, const ApplyParams& p, bool ref
         RG_CUDA(cudaGetLastError());
         return RG_OK;
     }
-    const bool slices = !empty_slab && use_slices(ctx, p.n_fields);
+    const bool slices = !empty_slab && use_slices(ctx, g, p.n_fields);
     const int W = pick_group_width(ctx, g, p.n_fields, slices);
     ApplyParams q = p;
     q.quads = nullptr;
