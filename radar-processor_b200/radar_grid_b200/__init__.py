@@ -23,7 +23,7 @@ from .products import (EARTH_RADIUS, EFFECTIVE_RADIUS_FACTOR, column_max, column
                        get_elevation_from_z_level)
 from .geotiff import apply_colormap_to_array
 from . import adapter
-from .engine import (ImageSpec, colormap_lut_bytes, CAPPI, PPI, LevelPick, ColumnMax, ColumnMean, ColumnMin, DeviceGeometry, GeometryCache, RangeRule, VolumePipeline, grid_fields,
+from .engine import (PreparedCall, prepare_grid_fields, ImageSpec, colormap_lut_bytes, CAPPI, PPI, LevelPick, ColumnMax, ColumnMean, ColumnMin, DeviceGeometry, GeometryCache, RangeRule, VolumePipeline, grid_fields,
                      run_products)
 
 __version__ = "0.1.0"
@@ -37,7 +37,7 @@ __all__ = [
     "get_elevation_from_z_level", "get_beam_height_difference", "compute_beam_height",
     "compute_beam_height_flat", "compute_beam_height_simple", "EARTH_RADIUS", "EFFECTIVE_RADIUS_FACTOR",
     # engine-level API
-    "DeviceGeometry", "grid_fields", "run_products", "RangeRule", "VolumePipeline", "GeometryCache",
+    "DeviceGeometry", "grid_fields", "prepare_grid_fields", "PreparedCall", "run_products", "RangeRule", "VolumePipeline", "GeometryCache",
     "ColumnMax", "ColumnMin", "ColumnMean", "CAPPI", "PPI", "LevelPick", "ImageSpec", "colormap_lut_bytes",
     "apply_colormap_to_array", "adapter",
     "set_device", "get_device", "pinned_empty",

@@ -535,7 +535,8 @@ def grid_fields(geom: DeviceGeometry, fields: Sequence, masks: Optional[Sequence
                 mask_invalid: Sequence[bool] | bool = False, rules: Sequence[RangeRule] = (),
                 fill_value: float = np.nan, want_grid: Sequence[bool] | bool = True, products: Sequence = (),
                 reference_order=False, ctx: Optional[N.Context] = None,
-                out_grids: Optional[Sequence] = None, out_products: Optional[Sequence] = None) -> Dict[str, object]:
+                out_grids: Optional[Sequence] = None, out_products: Optional[Sequence] = None,
+                _prepare_only: bool = False) -> Dict[str, object]:
     """
     One fused pass over the neighbour table for ``len(fields)`` (<= 8) fields.
 
@@ -659,9 +660,35 @@ def grid_fields(geom: DeviceGeometry, fields: Sequence, masks: Optional[Sequence
     parr = (N.Product * max(len(pstructs), 1))(*pstructs)
     args.rules = rarr
     args.products = parr
-    with N.torch_stream_order(ctx, device):
-        N.check(N.lib().rg_apply(ctx.handle, geom._h, C.byref(args), N.RG_DEVICE if device else N.RG_HOST))
-    return {"grids": grids, "products": pouts, "images": pimages, "_keep": (fheld, mheld, rheld, ikeep)}
+    result = {"grids": grids, "products": pouts, "images": pimages, "_keep": (fheld, mheld, rheld, ikeep)}
+    call = PreparedCall(ctx, geom, args, device, result, (fptr, mptr, gptr, rarr, parr, pstructs, rstructs))
+    if _prepare_only:
+        return call
+    call.launch()
+    return result
+
+
+class PreparedCall:
+    """A ``grid_fields`` call with every argument resolved and marshalled: ``launch()`` is one ``rg_apply`` and nothing
+    else.  For loops that grid volume after volume through the SAME buffers (a device-resident time series: new data
+    is written into the field tensors, the outputs are consumed, ``launch()`` again), where the host-side preparation of
+    ``grid_fields`` (product resolution, pointer marshalling: ~0.2 ms) would otherwise be paid per volume.
+    ``result`` is the dictionary ``grid_fields`` returns; its arrays are overwritten by every launch."""
+
+    def __init__(self, ctx, geom, args, device, result, keep):
+        self.ctx, self.geom, self.args, self.device, self.result, self._keep = ctx, geom, args, device, result, keep
+        self._space = N.RG_DEVICE if device else N.RG_HOST
+        self._fn = N.lib().rg_apply
+
+    def launch(self):
+        with N.torch_stream_order(self.ctx, self.device):
+            N.check(self._fn(self.ctx.handle, self.geom._h, C.byref(self.args), self._space))
+        return self.result
+
+
+def prepare_grid_fields(geom: DeviceGeometry, fields: Sequence, **kwargs) -> PreparedCall:
+    """``grid_fields`` with the same arguments, returning the marshalled call instead of running it."""
+    return grid_fields(geom, fields, _prepare_only=True, **kwargs)
 
 
 class GeometryCache:
