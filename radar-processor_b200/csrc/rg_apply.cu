@@ -64,6 +64,11 @@ int launch_sell_hi(Context* ctx, const ApplyParams& p);
 #define RG_PDL 1               // heavy_rows_kernel -> column kernel chained by programmatic dependent launch (cfg3 0.659 -> 0.650 ms,
                                //    cfg1 0.0525 -> 0.0465 ms)
 #endif
+#ifndef RG_ILPRE
+#define RG_ILPRE 0             // 1: slice-copy passes load the first batch of the NEXT level's pair slots into registers right after
+                               //    the current level's gathers, so that they travel while the row sums are reduced and stored.
+                               //    Measured: cfg3 0.760 vs 0.633 ms, cfg1 0.0462 vs 0.0432 ms: off
+#endif
 #ifndef RG_PRELOAD
 #define RG_PRELOAD 0           // N > 0: one- and two-field passes over the CSR copy keep the first N pairs of the NEXT level's row in
                                //    registers.  Measured with N = 3: cfg1 0.0466 vs 0.0465 ms, one field of cfg3 0.565 vs 0.540 ms: off.
@@ -1081,6 +1086,16 @@ __global__ void __launch_bounds__(kApplyThreads, F == 1 ? RG_MINBLOCKS_F1 : RG_M
             pre[j] = s_next + gl + j * W < e_next ? __ldcs(pairs + s_next + gl + j * W) : make_uint2(rec.null_gate, 0u);
     }
 
+    constexpr int PH = (IL && RG_ILPRE) ? 2 * RG_UNROLL - 1 : 0;
+    uint2 ipre[PH > 0 ? PH : 1];
+    auto il_preload = [&](uint32_t sn, uint32_t en) {          // (sn, en): the slice's bounds words of the level to preload
+        const uint32_t p0 = sn >> 1, mm = (en >> 1) - p0;
+        const uint2* nb = quads + (size_t)p0 * 32 + lane;
+#pragma unroll
+        for (int j = 0; j < PH; ++j) ipre[j] = (uint32_t)j < mm ? __ldcs(nb + j * 32) : make_uint2(rec.null_gate, 0u);
+    };
+    if constexpr (PH > 0) il_preload(s_next, e_next);
+
     size_t row = (size_t)p.lz_first * (size_t)p.ncol + (size_t)col - (size_t)p.ncol;
     for (int lz = p.lz_first; lz < p.lz_last; ++lz) {
         const uint32_t s = s_next, e = e_next;
@@ -1096,6 +1111,11 @@ __global__ void __launch_bounds__(kApplyThreads, F == 1 ? RG_MINBLOCKS_F1 : RG_M
 #pragma unroll
             for (int j = 0; j < NP; ++j)
                 pre[j] = s_next + gl + j * W < e_next ? __ldcs(pairs + s_next + gl + j * W) : make_uint2(rec.null_gate, 0u);
+        }
+        uint2 icur[PH > 0 ? PH : 1];
+        if constexpr (PH > 0) {
+#pragma unroll
+            for (int j = 0; j < PH; ++j) icur[j] = ipre[j];
         }
 #if RG_PREFETCH > 0
         if constexpr (IL) {   // level z+1's slots are contiguous: one 128-byte line per lane
@@ -1168,12 +1188,13 @@ __global__ void __launch_bounds__(kApplyThreads, F == 1 ? RG_MINBLOCKS_F1 : RG_M
                     need = lim > s + gl ? (lim - s - gl + W - 1) / W : 0u;
                     m = __reduce_max_sync(kFull, need);
                 }
-                auto head = [&](auto mm) {
+                auto head = [&](auto mm, auto first_tag) {
                     constexpr int M = decltype(mm)::value;
+                    constexpr bool FIRST = decltype(first_tag)::value && PH > 0;     // the batch preloaded during the previous level
                     uint2 hp[M];
 #pragma unroll
                     for (int j = 0; j < M; ++j) {
-                        if constexpr (IL) hp[j] = __ldcs(il_base + j * 32);
+                        if constexpr (IL) hp[j] = FIRST ? icur[j < PH ? j : 0] : __ldcs(il_base + j * 32);
                         else hp[j] = (uint32_t)j < need ? (j < NP ? cur[j < NP ? j : 0] : __ldcs(pairs + s + gl + j * W)) : make_uint2(rec.null_gate, 0u);
                     }
                     constexpr int C0 = M < U ? M : U;
@@ -1193,25 +1214,37 @@ __global__ void __launch_bounds__(kApplyThreads, F == 1 ? RG_MINBLOCKS_F1 : RG_M
                     }
                 };
                 static_assert(H == 7 || H == 5 || H == 3, "head sizes are written out below");
+                bool first = PH > 0;
                 if constexpr (IL) {
                     // the slot count is warp-uniform: full batches of H first, then ONE exactly sized batch, so that
                     // long rows never run slots that only hold padding
+                    if (PH > 0 && m > (uint32_t)H) {
+                        head(std::integral_constant<int, H>{}, std::true_type{});
+                        il_base += H * 32;
+                        m -= (uint32_t)H;
+                        first = false;
+                    }
                     while (m > (uint32_t)H) {
-                        head(std::integral_constant<int, H>{});
+                        head(std::integral_constant<int, H>{}, std::false_type{});
                         il_base += H * 32;
                         m -= (uint32_t)H;
                     }
                 }
+                auto head_k = [&](auto mm) {
+                    if constexpr (PH > 0) { if (first) { head(mm, std::true_type{}); return; } }
+                    head(mm, std::false_type{});
+                };
                 switch (m < (uint32_t)H ? m : (uint32_t)H) {
                     case 0: break;
-                    case 1: head(std::integral_constant<int, 1>{}); break;
-                    case 2: head(std::integral_constant<int, 2>{}); break;
-                    case 3: head(std::integral_constant<int, 3>{}); break;
-                    case 4: if constexpr (H >= 4) head(std::integral_constant<int, 4>{}); break;
-                    case 5: if constexpr (H >= 5) head(std::integral_constant<int, 5>{}); break;
-                    case 6: if constexpr (H >= 6) head(std::integral_constant<int, 6>{}); break;
-                    default: if constexpr (H >= 7) head(std::integral_constant<int, 7>{}); break;
+                    case 1: head_k(std::integral_constant<int, 1>{}); break;
+                    case 2: head_k(std::integral_constant<int, 2>{}); break;
+                    case 3: head_k(std::integral_constant<int, 3>{}); break;
+                    case 4: if constexpr (H >= 4) head_k(std::integral_constant<int, 4>{}); break;
+                    case 5: if constexpr (H >= 5) head_k(std::integral_constant<int, 5>{}); break;
+                    case 6: if constexpr (H >= 6) head_k(std::integral_constant<int, 6>{}); break;
+                    default: if constexpr (H >= 7) head_k(std::integral_constant<int, 7>{}); break;
                 }
+                if constexpr (PH > 0) il_preload(s_next, e_next);      // the next level's first batch travels during the reduce
                 if constexpr (!IL) {
                     if (m > (uint32_t)H) gather_run<F>(pairs, rec, min(s + gl + H * W, lim), lim, W, swv, sw);
                 }
@@ -1313,6 +1346,7 @@ __global__ void __launch_bounds__(kApplyThreads, F == 1 ? RG_MINBLOCKS_F1 : RG_M
                 }
             }
         };
+        if constexpr (PH > 0) { if (len == 0) il_preload(s_next, e_next); }   // empty level: nothing was summed, preload here
         if (IL && len == 0) finish(std::true_type{});
         else finish(std::false_type{});
     }
