@@ -54,7 +54,7 @@ def kernel_source_hash():
     capture (tools/ncu_summary.py --traffic), so a stale DRAM-traffic figure is never reported for a changed kernel."""
     import hashlib
     h = hashlib.sha256()
-    for f in ("rg_apply.cu", "rg_geometry.cu", "rg_api.cu", "rg_internal.cuh"):
+    for f in ("rg_apply.cu", "rg_duo.cu", "rg_geometry.cu", "rg_api.cu", "rg_internal.cuh", "rg_device.cuh"):
         with open(os.path.join(ROOT, "radar-processor_b200", "csrc", f), "rb") as fh:
             h.update(fh.read())
     return h.hexdigest()
@@ -292,6 +292,7 @@ def run_b200(args):
         same = all(torch.equal(out_grids[f].cpu().nan_to_num(-1e30), torch.from_numpy(pin_grids[f]).nan_to_num(-1e30))
                    for f in range(F))
 
+    duo_slots = dev.duo_slots
     ms_per_step = elapsed_ms / args.steps
     value = world * F * V / (ms_per_step * 1e-3)
     peak, peak_src = load_peaks()
@@ -314,11 +315,14 @@ def run_b200(args):
             "geometry_build_ms_device": info["build_ms"], "geometry_build_s_wall": build_wall,
             "geometry_candidates_per_pair": info["n_candidates"] / max(P, 1),
             "pack_ms_per_step": pack_ms / max(n_pack, 1), "apply_ms_per_step": apply_avg_ms,
+            # > 0: the pass read the column-pair copy of the table (apply_duo_kernel); lane-slots per pair = 12-byte entries
+            # (padding included) per 8-byte pair of the CSR table
+            "duo_slots": duo_slots, "duo_lane_slots_per_pair": (32.0 * duo_slots / P) if duo_slots > 0 else None,
             "device_vs_host_path_identical": bool(same),
         },
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": measured_traffic(spec.name),
-                     "kernel": "apply_columns_kernel", "algorithmic_bytes": b_alg, "peak_source": peak_src,
+                     "kernel": "apply_duo_kernel" if duo_slots > 0 else "apply_columns_kernel", "algorithmic_bytes": b_alg, "peak_source": peak_src,
                      "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None},
         "clocks": clocks,
         "e2e": {"value": world * F * V * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,

@@ -151,6 +151,13 @@ int rg_geometry_from_csr(rg_context* ctx, const rg_grid_spec* grid, const void* 
                          int32_t memspace, rg_geometry** out);
 
 int rg_geometry_get_info(const rg_geometry* geom, rg_geometry_info* info);
+
+/* State of the table's column-pair ("duo") copy, the layout rg_apply reads on tables of short rows, where neighbouring
+ * columns share most of their gates (the reference re-streams the whole table per field, interpolate.py:107-142):
+ * > 0 = built, that many 384-byte slots; 0 = not asked for yet; < 0 = not available for this table (rows not sorted by
+ * gate id, as in an imported reference table, or no room).  Context option "duo": 0 never, 1 auto (default: mean row
+ * below 96 pairs), 2 whenever the table allows it. */
+int rg_geometry_duo_slots(const rg_geometry* geom, int64_t* n_slots);
 /* Export as the reference's GridGeometry arrays (reference geometry.py:14-52).  Any pointer may be NULL. */
 int rg_geometry_export_csr(rg_context* ctx, const rg_geometry* geom, void* indptr, int32_t indptr_bits,
                            int32_t* gate_indices, float* weights, int32_t memspace);

@@ -17,8 +17,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SRC = [os.path.join(HERE, "csrc", f) for f in ("rg_api.cu", "rg_apply.cu", "rg_geometry.cu")]
-HDR = [os.path.join(HERE, "csrc", "rg_internal.cuh"), os.path.join(ROOT, "include", "radar_grid_b200.h")]
+SRC = [os.path.join(HERE, "csrc", f) for f in ("rg_api.cu", "rg_apply.cu", "rg_duo.cu", "rg_geometry.cu")]
+HDR = [os.path.join(HERE, "csrc", "rg_internal.cuh"), os.path.join(HERE, "csrc", "rg_device.cuh"), os.path.join(ROOT, "include", "radar_grid_b200.h")]
 LIBDIR = os.path.join(HERE, "lib")
 
 NVCC_FLAGS = [
@@ -61,24 +61,37 @@ def build(force=False, variant="", extra_flags=(), verbose=False):
         # GPU-minutes.  Say so loudly instead; build before taking the snapshot (or set RADAR_GRID_B200_REBUILD=1).
         sys.stderr.write(f"radar_grid_b200: {out} is older than its sources; using it as shipped (GPU box)\n")
         return out
-    # one nvcc per source file, in parallel (rg_apply.cu alone instantiates ~190 kernels), then one link step
+    # one nvcc per source file, in parallel (rg_apply.cu alone instantiates ~190 kernels), then one link step.  Objects are
+    # cached under /tmp by the digest of (source, headers, flags that reach the file): -DRG_DUO_* switches reach rg_duo.cu only,
+    # so an A/B variant of that kernel recompiles one file.
     import tempfile
     from concurrent.futures import ThreadPoolExecutor
-    flags = [f for f in NVCC_FLAGS if f != "-shared"] + list(extra_flags) + (["-Xptxas", "-v"] if verbose else [])
+    base_flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+    duo_flags = [f for f in extra_flags if f.startswith("-DRG_DUO_")]
+    common_flags = [f for f in extra_flags if not f.startswith("-DRG_DUO_")]
+    cache = os.environ.get("RG_OBJ_CACHE", os.path.join(tempfile.gettempdir(), "rg_objcache"))
+    os.makedirs(cache, exist_ok=True)
+    hdr_digest = hashlib.sha256(b"".join(open(h, "rb").read() for h in HDR)).hexdigest()
     with tempfile.TemporaryDirectory(prefix="rg_build_") as tmp:
         # rg_apply.cu is compiled as two translation units (field counts 1..4 + common code, and 5..8: see RG_PART there)
         jobs = []
         for f in SRC:
             base = os.path.basename(f)[:-3]
-            if base == "rg_apply":
-                jobs += [(f, os.path.join(tmp, base + "_lo.o"), ["-DRG_PART=1"]), (f, os.path.join(tmp, base + "_hi.o"), ["-DRG_PART=2"])]
-            else:
-                jobs.append((f, os.path.join(tmp, base + ".o"), []))
+            fl = common_flags + (duo_flags if base == "rg_duo" else [])
+            parts = [("_lo", ["-DRG_PART=1"]), ("_hi", ["-DRG_PART=2"])] if base == "rg_apply" else [("", [])]
+            for suffix, part_flags in parts:
+                key = hashlib.sha256((open(f, "rb").read().hex() + hdr_digest + " ".join(base_flags + fl + part_flags)).encode()).hexdigest()[:24]
+                jobs.append((f, os.path.join(cache, f"{base}{suffix}_{key}.o"), fl + part_flags))
         objs = [j[1] for j in jobs]
 
         def compile_one(job):
             src, obj, extra = job
-            return subprocess.run([nvcc] + flags + extra + ["-c", src, "-o", obj], capture_output=True, text=True)
+            if os.path.exists(obj) and not verbose and not force:
+                return subprocess.CompletedProcess([], 0, "", "")
+            res = subprocess.run([nvcc] + base_flags + extra + ["-c", src, "-o", obj + ".tmp"], capture_output=True, text=True)
+            if res.returncode == 0:
+                os.replace(obj + ".tmp", obj)
+            return res
 
         with ThreadPoolExecutor(max_workers=len(jobs)) as pool:
             results = list(pool.map(compile_one, jobs))

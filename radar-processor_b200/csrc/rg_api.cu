@@ -3,6 +3,7 @@
 //     [H2D fields/masks] -> K4 pack -> K5 apply (+K6 epilogue) -> [D2H grids/planes]
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -140,6 +141,8 @@ void free_geometry(Geometry* g)
     cudaFree(g->pairs);
     cudaFree(g->sell);
     for (auto& qc : g->quad) { cudaFree(qc.quads); cudaFree(qc.ptr); }
+    cudaFree(g->duo.slots);
+    cudaFree(g->duo.ptr);
     cudaFree(g->slice_base);
     cudaFree(g->heavy_rows);
     cudaFree(g->heavy_first);
@@ -445,6 +448,10 @@ int rg_context_create(int32_t device, void* stream, rg_context** out)
         ctx->own_stream = true;
     }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (const char* e = getenv("RADAR_GRID_B200_DUO")) {        // operations / A-B knob: the default of option "duo"
+        const int v = atoi(e);
+        if (v >= 0 && v <= 2) ctx->duo = v;
+    }
     *out = reinterpret_cast<rg_context*>(ctx);
     return RG_OK;
 }
@@ -455,7 +462,7 @@ int rg_context_destroy(rg_context* c)
     if (!ctx) return RG_OK;
     DeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (Scratch* s : {&ctx->records, &ctx->stage_in, &ctx->stage_out, &ctx->misc, &ctx->heavy, &ctx->luts})
+    for (Scratch* s : {&ctx->records, &ctx->stage_in, &ctx->stage_out, &ctx->misc, &ctx->heavy, &ctx->luts, &ctx->flags})
         if (s->ptr) cudaFree(s->ptr);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -508,6 +515,10 @@ int rg_context_set_option(rg_context* c, const char* key, int64_t value)
     if (strcmp(key, "apply_variant") == 0) ctx->apply_variant = value;
     else if (strcmp(key, "timing") == 0) ctx->timing = value;
     else if (strcmp(key, "sort_rows") == 0) ctx->sort_rows = value;
+    else if (strcmp(key, "duo") == 0) {
+        if (value < 0 || value > 2) return fail(RG_ERR_INVALID, "duo must be 0 (off), 1 (auto) or 2 (whenever the table allows it)");
+        ctx->duo = value;
+    }
     else if (strcmp(key, "group_width") == 0) {
         if (value != 0 && value != 4 && value != 8 && value != 16 && value != 32)
             return fail(RG_ERR_INVALID, "group_width must be 0, 4, 8, 16 or 32");
@@ -794,6 +805,14 @@ int rg_geometry_get_info(const rg_geometry* geom, rg_geometry_info* info)
     return RG_OK;
 }
 
+int rg_geometry_duo_slots(const rg_geometry* geom, int64_t* n_slots)
+{
+    const Geometry* g = reinterpret_cast<const Geometry*>(geom);
+    if (!g || !n_slots) return fail(RG_ERR_INVALID, "NULL argument");
+    *n_slots = g->duo.n_slots;
+    return RG_OK;
+}
+
 int rg_geometry_export_csr(rg_context* c, const rg_geometry* geom, void* indptr, int32_t indptr_bits,
                            int32_t* gate_indices, float* weights, int32_t memspace)
 {
@@ -1035,6 +1054,13 @@ int rg_apply(rg_context* c, const rg_geometry* geom, const rg_apply_args* a, int
     RG_TRY(ensure(ctx, ctx->records, (size_t)(G + 1) * FP * 4 + 1024));
     pk.records = (float*)ctx->records.ptr;
     pk.records_b = (float*)((char*)ctx->records.ptr + records_b_offset(F, G));
+    if (ctx->flags.ptr == nullptr || ctx->epoch == 0xFFFFFFFFu) {   // first call (or the epoch counter wrapped): clear the stamp
+        RG_TRY(ensure(ctx, ctx->flags, 256));
+        RG_CUDA(cudaMemsetAsync(ctx->flags.ptr, 0, 256, ctx->stream));
+        ctx->epoch = 0;
+    }
+    pk.nonfinite = (uint32_t*)ctx->flags.ptr;
+    pk.epoch = ++ctx->epoch;
     RG_TRY(launch_pack(ctx, pk));
 
     // ---- outputs
@@ -1080,6 +1106,8 @@ int rg_apply(rg_context* c, const rg_geometry* geom, const rg_apply_args* a, int
     ap.slice_base = g->slice_base;
     ap.slices_per_level = g->slices_per_level;
     ap.null_gate = (uint32_t)G;
+    ap.nonfinite = pk.nonfinite;
+    ap.epoch = pk.epoch;
     RG_TRY(bind_record_textures(ctx, pk.records, pk.records_b, F, G));
     ap.tex_a = ctx->tex_a;
     ap.tex_b = ctx->tex_b;

@@ -566,6 +566,106 @@ __global__ void __launch_bounds__(128) quad_fill_kernel(const uint32_t* __restri
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Column-pair ("duo") copy of the table for apply_duo_kernel (rg_duo.cu; layout in rg_internal.cuh).
+// One thread per group = the columns (x, 2yp) and (x, 2yp + 1) at one level; the 8 groups of a slice sit in 8 consecutive
+// threads.  The two rows are merged by gate id (both are sorted: sort_rows_kernel; a table imported in another order
+// raises `unsorted` and does not get a duo copy).  Rows longer than kHeavyRow stay out (heavy_rows_kernel sums them).
+// ------------------------------------------------------------------------------------------------------
+struct DuoGroup {
+    uint32_t s0, e0, s1, e1;
+    int k;                                 // group within the slice
+    int64_t q;                             // slice
+    bool heavy;
+};
+
+__device__ __forceinline__ DuoGroup duo_group(const uint32_t* __restrict__ indptr, int nx, int ny, int nyp, int qxn, int64_t n_groups,
+                                              uint32_t heavy_len)
+{
+    DuoGroup g{0, 0, 0, 0, 0, 0, false};
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    g.q = t >> 3;
+    g.k = (int)(t & 7);
+    if (t >= n_groups) return g;
+    const int64_t line = g.q / qxn;                            // lz * nyp + yp
+    const int qx = (int)(g.q - line * qxn);
+    const int64_t lz = line / nyp;
+    const int yp = (int)(line - lz * nyp);
+    const int x = qx * 8 + g.k, y0 = 2 * yp;
+    if (x >= nx) return g;
+    const size_t row0 = ((size_t)lz * (size_t)ny + (size_t)y0) * (size_t)nx + (size_t)x;
+    g.s0 = indptr[row0];
+    g.e0 = indptr[row0 + 1];
+    if (g.e0 - g.s0 > heavy_len) { g.heavy = true; g.e0 = g.s0; }
+    if (y0 + 1 < ny) {
+        g.s1 = indptr[row0 + (size_t)nx];
+        g.e1 = indptr[row0 + (size_t)nx + 1];
+        if (g.e1 - g.s1 > heavy_len) { g.heavy = true; g.e1 = g.s1; }
+    }
+    return g;
+}
+
+__global__ void __launch_bounds__(256) duo_count_kernel(const uint32_t* __restrict__ indptr, const uint2* __restrict__ pairs, int nx, int ny,
+                                                        int nyp, int qxn, int64_t n_groups, uint32_t heavy_len,
+                                                        uint32_t* __restrict__ counts, uint8_t* __restrict__ heavy,
+                                                        unsigned int* __restrict__ unsorted)
+{
+    const DuoGroup g = duo_group(indptr, nx, ny, nyp, qxn, n_groups, heavy_len);
+    uint32_t i = g.s0, j = g.s1, n = 0;
+    uint32_t prev0 = 0, prev1 = 0;
+    bool bad = false;
+    while (i < g.e0 || j < g.e1) {
+        const uint32_t a = i < g.e0 ? pairs[i].x : 0xFFFFFFFFu, b = j < g.e1 ? pairs[j].x : 0xFFFFFFFFu;
+        if (a <= b) { bad |= i > g.s0 && a <= prev0; prev0 = a; ++i; }
+        if (b <= a) { bad |= j > g.s1 && b <= prev1; prev1 = b; ++j; }
+        ++n;
+    }
+    if (bad) atomicAdd(unsorted, 1u);
+    uint32_t m = (n + 3u) / 4u;
+    uint32_t hv = g.heavy ? 1u : 0u;
+#pragma unroll
+    for (int off = 1; off <= 4; off <<= 1) {
+        m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, off));
+        hv |= __shfl_xor_sync(0xFFFFFFFFu, hv, off);
+    }
+    if (g.k == 0 && g.q * 8 < n_groups) {
+        counts[g.q] = m;
+        heavy[g.q] = (uint8_t)hv;
+    }
+}
+
+__global__ void __launch_bounds__(256) duo_fill_kernel(const uint32_t* __restrict__ indptr, const uint2* __restrict__ pairs, int nx, int ny,
+                                                       int nyp, int qxn, int64_t n_groups, uint32_t heavy_len,
+                                                       const uint32_t* __restrict__ offs, const uint32_t* __restrict__ counts,
+                                                       const uint8_t* __restrict__ heavy, uint32_t null_gate,
+                                                       uint32_t* __restrict__ slots, uint32_t* __restrict__ duo_ptr)
+{
+    const DuoGroup g = duo_group(indptr, nx, ny, nyp, qxn, n_groups, heavy_len);
+    if (g.q * 8 >= n_groups) return;
+    const uint32_t m = counts[g.q], o = offs[g.q];
+    if (g.k == 0) {
+        duo_ptr[g.q] = (o << 1) | heavy[g.q];
+        if ((g.q + 1) * 8 >= n_groups) duo_ptr[g.q + 1] = (o + m) << 1;
+    }
+    const uint32_t absent = 0x80000000u;                       // -0.0f: see rg_duo.cu
+    uint32_t i = g.s0, j = g.s1, n = 0;
+    auto put = [&](uint32_t gate, uint32_t w0, uint32_t w1) {
+        uint32_t* slot = slots + (size_t)(o + (n >> 2)) * 96;
+        const uint32_t l = (uint32_t)g.k * 4u + (n & 3u);
+        slot[l] = gate;
+        slot[32 + 2 * l] = w0;
+        slot[32 + 2 * l + 1] = w1;
+        ++n;
+    };
+    while (i < g.e0 || j < g.e1) {
+        const uint2 a = i < g.e0 ? pairs[i] : make_uint2(0xFFFFFFFFu, 0u), b = j < g.e1 ? pairs[j] : make_uint2(0xFFFFFFFFu, 0u);
+        if (a.x == b.x) { put(a.x, a.y, b.y); ++i; ++j; }
+        else if (a.x < b.x) { put(a.x, a.y, absent); ++i; }
+        else { put(b.x, absent, b.y); ++j; }
+    }
+    while (n < m * 4u) put(null_gate, absent, absent);        // idle lanes: the all-masked record
+}
+
 // ---- heavy rows --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) heavy_list_kernel(const uint32_t* __restrict__ indptr, int64_t n_rows, uint32_t heavy_len,
                                                          uint32_t capacity, uint32_t* __restrict__ rows, unsigned int* __restrict__ count)
@@ -695,6 +795,67 @@ int ensure_quads(Context* ctx, Geometry* g, int W, const Geometry::QuadCopy** ou
     qc.n_slots = (int64_t)total;
     qc.quads_x = quads_x;
     g->info.device_bytes += (int64_t)((size_t)total * 32 * sizeof(uint2) + ((size_t)n_slices + 1) * sizeof(uint32_t));
+    return RG_OK;
+}
+
+int ensure_duo(Context* ctx, Geometry* g, const Geometry::DuoCopy** out)
+{
+    std::lock_guard<std::mutex> lock(g->quad_mu);
+    Geometry::DuoCopy& dc = g->duo;
+    *out = &dc;
+    if (dc.ptr != nullptr) return RG_OK;
+    *out = nullptr;
+    if (dc.n_slots < 0) return RG_OK;                          // found unsuitable earlier
+    const int nx = g->grid.nx, ny = g->grid.ny;
+    const int nyp = (ny + 1) / 2, qxn = (nx + 7) / 8;
+    const int64_t n_slices = (int64_t)g->n_levels * nyp * qxn, n_groups = n_slices * 8;
+    if (n_slices == 0 || g->n_pairs == 0) { dc.n_slots = -1; return RG_OK; }
+    DevBuf<uint32_t> counts, offs, dptr;
+    DevBuf<uint8_t> heavy;
+    DevBuf<unsigned long long> tmp;
+    DevBuf<unsigned int> unsorted;
+    RG_CUDA(dptr.alloc((size_t)n_slices + 1));
+    RG_CUDA(counts.alloc((size_t)n_slices));
+    RG_CUDA(offs.alloc((size_t)n_slices + 1));
+    RG_CUDA(heavy.alloc((size_t)n_slices));
+    RG_CUDA(tmp.alloc((size_t)(n_slices / kScanTile + 4)));
+    RG_CUDA(unsorted.alloc(1));
+    RG_CUDA(cudaMemsetAsync(unsorted.p, 0, sizeof(unsigned int), ctx->stream));
+    const unsigned blocks = (unsigned)((n_groups + 255) / 256);
+    duo_count_kernel<<<blocks, 256, 0, ctx->stream>>>(g->indptr, g->pairs, nx, ny, nyp, qxn, n_groups, kHeavyRow, counts.p, heavy.p,
+                                                     unsorted.p);
+    ctx->launches++;
+    RG_CUDA(cudaGetLastError());
+    uint64_t total = 0;
+    RG_TRY(exclusive_scan_u32(ctx, counts.p, offs.p, n_slices, tmp.p, &total));
+    unsigned int n_unsorted = 0;
+    RG_CUDA(cudaMemcpy(&n_unsorted, unsorted.p, sizeof(n_unsorted), cudaMemcpyDeviceToHost));
+    // Not for this table: rows in another order than by gate id (an imported table), more slots than a 31-bit slot index
+    // holds, or no room next to the table.  Whether the merge pays is decided by the caller from the row lengths alone
+    // (launch_apply: tables of short rows, where the pass is bound by latency and L1 traffic and the kernel won every
+    // measurement -- cfg1: 0.89 entries per pair, 0.0383 against 0.0445 ms; cfg3: 0.74, 0.606 against 0.642 ms), so that
+    // all z-slabs of one grid take the same kernel and stay bit-identical to the unsharded pass.
+    size_t free_b = 0, total_b = 0;
+    RG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t need_b = (size_t)total * 96 * sizeof(uint32_t);
+    if (n_unsorted != 0 || total >= (1ull << 31) || need_b + (size_t)(1ull << 30) > free_b) {
+        dc.n_slots = -1;
+        return RG_OK;
+    }
+    DevBuf<uint32_t> slots;
+    RG_CUDA(slots.alloc((size_t)total * 96));
+    duo_fill_kernel<<<blocks, 256, 0, ctx->stream>>>(g->indptr, g->pairs, nx, ny, nyp, qxn, n_groups, kHeavyRow, offs.p, counts.p, heavy.p,
+                                                    (uint32_t)g->n_gates, slots.p, dptr.p);
+    ctx->launches++;
+    RG_CUDA(cudaGetLastError());
+    RG_CUDA(cudaStreamSynchronize(ctx->stream));
+    dc.slots = slots.p; slots.p = nullptr;
+    dc.ptr = dptr.p; dptr.p = nullptr;
+    dc.n_slots = (int64_t)total;
+    dc.qx = qxn;
+    dc.nyp = nyp;
+    g->info.device_bytes += (int64_t)(need_b + ((size_t)n_slices + 1) * sizeof(uint32_t));
+    *out = &dc;
     return RG_OK;
 }
 

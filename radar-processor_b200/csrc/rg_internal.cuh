@@ -70,6 +70,19 @@ struct Geometry {
         int64_t n_slots = 0;
         int32_t quads_x = 0;
     } quad[4];
+    // Column-pair ("duo") copy for the multi-field kernel of rg_duo.cu: a group of 4 lanes owns the two columns (x, 2yp)
+    // and (x, 2yp + 1); the rows of the two columns at one level are merged by gate id into entries {gate, w0, w1}
+    // (w = 0 where the gate is not in that column's row), so every gate record is gathered once for both columns.
+    // The 8 groups of a warp (8 adjacent x) at one level form a slice; slot j of a slice holds entries [4j, 4j+4) of
+    // each of its groups in lane order: 32 gate ids (128 B) followed by 32 weight pairs (256 B).  Idle lanes point at
+    // the all-masked record with absent weights (-0.0).  Built on first use under quad_mu; n_slots < 0: not available for
+    // this table (rows not sorted by gate id, or no room).
+    struct DuoCopy {
+        uint32_t* slots = nullptr;       // [n_slots][96]
+        uint32_t* ptr = nullptr;         // [n_levels * nyp * qx + 1]: (first slot << 1) | slice has a heavy row
+        int64_t n_slots = 0;
+        int32_t qx = 0, nyp = 0;
+    } duo;
     std::mutex quad_mu;
     // Rows longer than kHeavyRow (voxels next to the radar see the first gates of every ray): sorted row ids, the
     // chunks (<= kHeavyChunk pairs) they are cut into, built once per table under quad_mu (ensure_heavy).
@@ -117,6 +130,9 @@ struct Context {
     Scratch misc;
     Scratch luts;                        // colormap LUTs of the image products of a call
     Scratch heavy;                       // per-chunk partial sums of the heavy rows: float[n_heavy_chunks][2 * F]
+    Scratch flags;                       // uint32: epoch of the last volume that held an UNMASKED non-finite value (see PackParams)
+    uint32_t epoch = 0;                  // counts rg_apply calls of this context
+    int64_t duo = 1;                     // option "duo": 0 = never use the column-pair kernel, 1 = auto (tables of short rows), 2 = whenever the table allows it
 };
 
 int ensure(Context* ctx, Scratch& s, size_t bytes);
@@ -198,6 +214,11 @@ struct ApplyParams {
     const uint2* heavy_chunks;
     float* heavy_part;                    // [n_heavy_chunks][2 * n_fields]: sum(w*v) per field, then sum(w) per field
     int32_t n_heavy, n_heavy_chunks;
+    const uint32_t* duo;                  // column-pair copy of the table (rg_duo.cu), nullptr = not in use
+    const uint32_t* duo_ptr;
+    int32_t duo_qx, duo_nyp;
+    const uint32_t* nonfinite;            // == epoch: this volume holds an unmasked non-finite value (zero weights must not touch it)
+    uint32_t epoch;
     unsigned long long tex_a, tex_b;      // texture objects over records / records_b (RG_TEX builds)
     int64_t ncol;                         // ny*nx
     int32_t nx, ny;
@@ -229,6 +250,12 @@ struct PackParams {
     uint32_t rule_bits[RG_MAX_RULES];
     float* records;
     float* records_b;
+    // An unmasked NaN / inf value propagates into every voxel whose row holds the gate (interpolate.py:78-82).  The
+    // column-pair kernel multiplies such a value by a ZERO weight for the column that does not hold the gate, so it has to
+    // know: the pack kernel stamps *nonfinite with the call's epoch when it sees one, and the kernel then takes its
+    // predicated path.
+    uint32_t* nonfinite;
+    uint32_t epoch;
 };
 
 // ---- launchers (defined in the .cu files) -----------------------------------------------------------
@@ -247,6 +274,8 @@ int finalize_geometry_stats(Context* ctx, Geometry* g);
 int build_sell(Context* ctx, Geometry* g);
 int ensure_quads(Context* ctx, Geometry* g, int W, const Geometry::QuadCopy** out);
 int ensure_heavy(Context* ctx, Geometry* g);
+int ensure_duo(Context* ctx, Geometry* g, const Geometry::DuoCopy** out);
+int launch_duo(Context* ctx, const ApplyParams& p);      // rg_duo.cu: the column-pair kernel alone (no heavy launch, no timers)
 int exclusive_scan_u32(Context* ctx, const uint32_t* in, uint32_t* out, int64_t n, unsigned long long* tmp, uint64_t* total_host);
 void linspace_f32(double start, double stop, int num, float* out);
 

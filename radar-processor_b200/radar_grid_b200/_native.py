@@ -95,6 +95,7 @@ _PROTOTYPES = {
     "rg_geometry_from_csr": (C.c_int, [C.c_void_p, C.POINTER(GridSpec), C.c_void_p, C.c_int32, C.c_void_p,
                                        C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_void_p)]),
     "rg_geometry_get_info": (C.c_int, [C.c_void_p, C.POINTER(GeometryInfo)]),
+    "rg_geometry_duo_slots": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "rg_geometry_export_csr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                          C.c_int32]),
     "rg_geometry_destroy": (C.c_int, [C.c_void_p]),

@@ -136,6 +136,13 @@ class DeviceGeometry:
         return self._info
 
     @property
+    def duo_slots(self) -> int:
+        """> 0: slots of the column-pair copy the multi-field pass reads; 0: not built yet; < 0: not available for this table."""
+        n = C.c_int64(0)
+        N.check(N.lib().rg_geometry_duo_slots(self._h, C.byref(n)))
+        return int(n.value)
+
+    @property
     def n_pairs(self) -> int:
         return int(self.info["n_pairs"])
 

@@ -78,7 +78,7 @@ def rewrite_launches(src: str) -> str:
 def main():
     os.makedirs(OUT, exist_ok=True)
     cpps = []
-    for f in ("rg_api.cu", "rg_apply.cu", "rg_geometry.cu"):
+    for f in ("rg_api.cu", "rg_apply.cu", "rg_duo.cu", "rg_geometry.cu"):
         src = open(os.path.join(CSRC, f)).read()
         dst = os.path.join(OUT, f.replace(".cu", ".cpp"))
         text = rewrite_launches(src)

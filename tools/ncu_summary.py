@@ -52,7 +52,7 @@ def main():
         import hashlib, json, os
         root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
         hh = hashlib.sha256()
-        for f in ("rg_apply.cu", "rg_geometry.cu", "rg_api.cu", "rg_internal.cuh"):
+        for f in ("rg_apply.cu", "rg_duo.cu", "rg_geometry.cu", "rg_api.cu", "rg_internal.cuh", "rg_device.cuh"):
             hh.update(open(os.path.join(root, "radar-processor_b200", "csrc", f), "rb").read())
         to_bytes = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
         tot = sum(float(r[hdr.index(k)]) * to_bytes[units[hdr.index(k)]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
