@@ -1458,11 +1458,15 @@ int launch_apply(Context* ctx, const Geometry* g, const ApplyParams& p, bool ref
     q.quads_x = 0;
     q.heavy_rows = nullptr; q.heavy_first = nullptr; q.heavy_chunks = nullptr; q.heavy_part = nullptr;
     q.n_heavy = 0; q.n_heavy_chunks = 0;
-    // Several fields over rows that overlap: the column-pair kernel (rg_duo.cu) over the merged rows of two adjacent columns
+    // Rows that overlap with their neighbour's: the column-pair kernel (rg_duo.cu) over the merged rows of two adjacent columns.
+    // Auto: tables whose mean row is below 160 pairs (group widths 4 and 8).  Measured against the column-group kernel: cfg3
+    // (mean 40 pairs, five fields) 0.604 / 0.640 ms; cfg1 (16 pairs, one field) 0.0378 / 0.0444 ms; cfg5 (110 pairs, one field,
+    // 226 GB of table slab by slab) 35.2 / 41.9 ms.  The decision depends on the row lengths only, so the z-slabs of one grid
+    // take the same kernel and stay bit-identical to the unsharded pass.
     bool duo = false;
     q.duo = nullptr; q.duo_ptr = nullptr; q.duo_qx = 0; q.duo_nyp = 0;
     if (!empty_slab && ctx->duo != 0 && ctx->apply_variant == 0 && ctx->group_width == 0 &&
-        (ctx->duo >= 2 || (W == 4 && p.n_fields >= RG_DUO_MIN_FIELDS))) {
+        (ctx->duo >= 2 || (W <= 8 && p.n_fields >= RG_DUO_MIN_FIELDS))) {
         const Geometry::DuoCopy* dc = nullptr;
         RG_TRY(ensure_duo(ctx, const_cast<Geometry*>(g), &dc));
         if (dc != nullptr) {                            // nullptr: the table does not lend itself to it

@@ -37,7 +37,12 @@ namespace rg {
 #define RG_DUO_PIPE 2          // 1: the entries of the NEXT chunk of U slots (of this level, or the first chunk of the next level)
                                //    are loaded while the current chunk's records are gathered and summed: the entry loads (23 % of
                                //    all stall samples of the batch form, profiles/r02_duo_h7u4_apply.md) leave the dependent chain.
+                               // 2: batches of H as in 0; the first batch of the NEXT LEVEL is loaded right after the last sums of the
+                               //    current one and travels during the reduce and the epilogue (0.617 -> 0.606 ms)
                                // 0: batches of H entry loads, gathers in chunks of U (the first version)
+                               // (a form 3 -- the previous level's quotients, stores and product state executed under the first gathers
+                               //  of the next level -- was built and measured at 0.71-0.78 ms: spills, and a predicated first chunk
+                               //  that runs whether the level needs it or not; removed)
 #endif
 #ifndef RG_DUO_ENTRY_LD
 #define RG_DUO_ENTRY_LD 2      // how the entries (read once, by one warp) are loaded: 0 = ld.global.cs (evict first), 1 = ld.global.cg
