@@ -20,4 +20,4 @@ timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --mas
 python -c "
 import json; d=json.load(open('gpurun_out/bench_n$N.json'))
 print({k: d[k] for k in ('value','ms_per_step','n_gpus','gpu_launches','scaling')}); print(d['roofline']['frac'], 'e2e', d['e2e']['value'], d['e2e']['ms_per_step'], 'products-only', d['e2e_products_only']['value'], d['e2e_products_only']['ms_per_step'], d['clocks']); print(d['zslab'])"; tail -3 gpurun_out/bench_n$N.err | cut -c1-300
-echo "== pcie ceiling, up to $N concurrent processes"; timeout 300 python tools/pcie_ceiling.py --out gpurun_out/pcie_ceiling_n$N.json
+if [ -z "${SKIP_PCIE:-}" ]; then echo "== pcie ceiling, up to $N concurrent processes"; timeout 300 python tools/pcie_ceiling.py --out gpurun_out/pcie_ceiling_n$N.json; fi
