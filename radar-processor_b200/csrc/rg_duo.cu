@@ -6,10 +6,13 @@
 // Why: the column-group kernel of rg_apply.cu gathers a gate record once per PAIR, and its time is the bytes those
 // gathers pull through the L1 data pipe.  But neighbouring voxels see almost the same gates: at
 // cfg3 the rows of the columns (x, y) and (x, y + 1) share 61 % of their gates.  The duo copy of the table (ensure_duo,
-// rg_geometry.cu) merges the two rows by gate id into entries {gate, w0, w1}; a lane gathers the record ONCE and feeds
-// both columns with one packed FFMA2 / FADD2 per field (fma.rn.f32x2, add.rn.f32x2: sm_100+), the weights arriving as
-// the register pair the 64-bit load wrote.  Per pair that is 0.57 x the record gathers, 0.6 x the instructions and, with
-// 12-byte entries over 1.6 pairs each, 0.85 x the table bytes of the warp-slice copy.
+// rg_geometry.cu) merges the two rows by gate id into entries {gate, w0, w1}; a lane gathers the record ONCE and adds
+// w0 * v / w1 * v to the sums of both columns (per field one predicate, 2 FFMA, 2 FADD; the packed fma.rn.f32x2 form is
+// used in the mask-bit record layout only: ptxas does not predicate a packed instruction in place).  Per pair that is
+// 0.57 x the record gathers and, with 12-byte entries over 1.6 pairs each, 0.85 x the table bytes of the warp-slice copy.
+// The kernel is latency-bound (issue 58 %, L1 61 %, DRAM 54 %): what it needs is loads in flight -- batches of 7 entry
+// loads, gathers in chunks of 4, and the first batch of the next level loaded before the reduce and the epilogue of the
+// current one (DESIGN.md section 6 has the measured history of every choice).
 //
 // Mapping: a group of 4 lanes owns the columns (x, 2yp) and (x, 2yp + 1); the 8 groups of a warp are adjacent in x; the
 // 4 warps of a CTA take 4 consecutive yp: an 8 x 8 patch of columns per CTA.  Lane j of a group takes entries j, j + 4,
@@ -36,7 +39,7 @@ namespace rg {
 #ifndef RG_DUO_PIPE
 #define RG_DUO_PIPE 2          // 1: the entries of the NEXT chunk of U slots (of this level, or the first chunk of the next level)
                                //    are loaded while the current chunk's records are gathered and summed: the entry loads (23 % of
-                               //    all stall samples of the batch form, profiles/r02_duo_h7u4_apply.md) leave the dependent chain.
+                               //    all stall samples of the batch form, profiles/r02_duo_batch_h7u4_apply.md) leave the dependent chain.
                                // 2: batches of H as in 0; the first batch of the NEXT LEVEL is loaded right after the last sums of the
                                //    current one and travels during the reduce and the epilogue (0.617 -> 0.606 ms)
                                // 0: batches of H entry loads, gathers in chunks of U (the first version)
