@@ -859,6 +859,21 @@ __global__ void __launch_bounds__(kApplyThreads, F == 1 ? RG_MINBLOCKS_F1 : RG_M
         // output is the fill value; with a NaN fill the running maximum is not touched either.
         auto finish = [&](auto empty_tag) {
             constexpr bool EMPTY = decltype(empty_tag)::value;
+            if constexpr (PROD) {                              // the generic product list: both states of the lane in one pass
+                float vv[NO];
+                bool on[NO];
+#pragma unroll
+                for (int k = 0; k < NO; ++k) {
+                    on[k] = owner && gl + k * W < F;
+                    vv[k] = !EMPTY && b[k] > 0.f ? fast_div(a[k], b[k]) : p.fill;              // interpolate.py:99-102
+                    if (on[k]) {
+                        float* const dst = QS ? p.grid_out[gl + k * W] : out[k];
+                        if (dst != nullptr) __stcs(dst + row, vv[k]);
+                    }
+                }
+                ColumnState::update_words_n<NO>(p.prod, sm_state, NO, p.z_begin + lz, vv, on);
+                return;
+            }
 #pragma unroll
             for (int k = 0; k < NO; ++k) {
                 if (owner && gl + k * W < F) {
@@ -866,9 +881,6 @@ __global__ void __launch_bounds__(kApplyThreads, F == 1 ? RG_MINBLOCKS_F1 : RG_M
                     // QS: pointer from the parameter bank, no register held across levels
                     float* const dst = QS ? p.grid_out[gl + k * W] : out[k];
                     if (dst != nullptr) __stcs(dst + row, v);
-                    if constexpr (PROD) {
-                        ColumnState::update_words(p.prod, sm_state, k, NO, p.z_begin + lz, v);
-                    }
                     if constexpr (PSIG == 2) {
                         const int z = p.z_begin + lz;
                         if constexpr (QS) {

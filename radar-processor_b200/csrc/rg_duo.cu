@@ -408,6 +408,21 @@ __global__ void __launch_bounds__(kApplyThreads, RG_DUO_MINBLOCKS) apply_duo_ker
         // the fill value; with a NaN fill the running maximum is not touched either.
         auto finish = [&](auto empty_tag) {
             constexpr bool EMPTY = decltype(empty_tag)::value;
+            if constexpr (PROD) {                              // the generic product list: all states of the lane in one pass
+                float vv[HF];
+                bool on[HF];
+#pragma unroll
+                for (int k = 0; k < HF; ++k) {
+                    on[k] = col_ok && f0 + k < F;
+                    vv[k] = !EMPTY && b[k] > 0.f ? fast_div(a[k], b[k]) : p.fill;              // interpolate.py:99-102
+                    if (on[k]) {
+                        float* const dst = p.grid_out[f0 + k];
+                        if (dst != nullptr) __stcs(dst + row, vv[k]);
+                    }
+                }
+                ColumnState::update_words_n<HF>(p.prod, sm_state, HF, p.z_begin + lz, vv, on);
+                return;
+            }
 #pragma unroll
             for (int k = 0; k < HF; ++k) {
                 const int f = f0 + k;
@@ -415,7 +430,6 @@ __global__ void __launch_bounds__(kApplyThreads, RG_DUO_MINBLOCKS) apply_duo_ker
                     const float v = !EMPTY && b[k] > 0.f ? fast_div(a[k], b[k]) : p.fill;      // interpolate.py:99-102
                     float* const dst = p.grid_out[f];          // from the parameter bank: no register held across levels
                     if (dst != nullptr) __stcs(dst + row, v);
-                    if constexpr (PROD) ColumnState::update_words(p.prod, sm_state, k, HF, p.z_begin + lz, v);
                     if constexpr (PSIG == 2) {
                         const int z = p.z_begin + lz;
                         float* const qs = sm_state + k * kApplyThreads + threadIdx.x;
