@@ -36,12 +36,6 @@ def build(spec, gates, weighting="barnes2", alt=0, **kw):
                                    toa=toa, **kw)
 
 
-def launches_of(dev, fn):
-    before = dev.ctx.kernel_launches()
-    out = fn()
-    return out, dev.ctx.kernel_launches() - before
-
-
 @pytest.mark.parametrize("spec_name,weighting,alt", [("tiny", "barnes2", 0), ("tiny", "cressman", 0), ("tiny", "nearest", 0),
                                                      ("tiny", "barnes2", 350), ("small", "barnes2", 0)])
 def test_duo_grids_match_the_reference_goldens(spec_name, weighting, alt):
